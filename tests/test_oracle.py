@@ -1,0 +1,78 @@
+"""Pins the CPU oracle (oracle/ngsld_oracle.c) to the reference: md5 equality with outputs of the
+unmodified reference binary on every golden fixture, GSL's own known answer for the taus generator,
+and -- when oracle/_ref/ngsLD is present -- a live run of the reference itself."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import O
+
+CASES = [(fx, v) for fx, d in H.MANIFEST["fixtures"].items() for v in d["variants"]]
+
+
+def test_taus_known_answer():
+    # GSL rng/test.c: rng_test(gsl_rng_taus, 1, 10000, 2733957125UL)
+    t = O.Taus()
+    O.lib().orc_taus_set(C.byref(t), 1)
+    for _ in range(9999):
+        O.lib().orc_taus_get(C.byref(t))
+    assert O.lib().orc_taus_get(C.byref(t)) == 2733957125
+
+
+def test_taus_seed_zero_is_one():
+    a, b = O.Taus(), O.Taus()
+    O.lib().orc_taus_set(C.byref(a), 0)
+    O.lib().orc_taus_set(C.byref(b), 1)
+    assert [O.lib().orc_taus_get(C.byref(a)) for _ in range(5)] == [O.lib().orc_taus_get(C.byref(b)) for _ in range(5)]
+
+
+@pytest.mark.parametrize("fx,variant", CASES)
+def test_oracle_matches_reference_golden(fx, variant, tmp_path_factory):
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"][fx]["variants"][variant]
+    got = H.oracle_tsv(fx, tmp, v["flags"], use_pos=v["pos"], geno=v.get("geno"), n_threads=os.cpu_count() or 4)
+    gold = H.golden_bytes(fx, variant)
+    if gold is not None:
+        assert H.md5(gold) == v["md5"]
+        assert got == gold
+    assert H.md5(got) == v["md5"]
+    assert got.count(b"\n") - 1 == v["rows"]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/ngsLD not built (needs /root/reference)")
+@pytest.mark.parametrize("threads", [1, 3])
+def test_reference_binary_live(threads, tmp_path):
+    """The reference itself, run here: thread count must not change the sorted output, and the
+    oracle restatement must equal it byte for byte on a fresh random fixture (not a stored one)."""
+    GL, pos = H.gen_synth.synth(50, 17, 99)
+    geno = str(tmp_path / "live.glf")
+    H.gen_synth.write(geno, GL, pos)
+    out = str(tmp_path / "ref.ld")
+    O.run_ref(["--geno", geno, "--probs", "--n_ind", "17", "--n_sites", "50", "--pos", geno + ".pos",
+               "--max_kb_dist", "7", "--extend_out"], out, n_threads=threads)
+    ref = open(out, "rb").read()
+    gl, expg, maf = O.preprocess(GL)
+    labels, dist = O.read_pos(geno + ".pos")
+    mine = str(tmp_path / "orc.ld")
+    O.run(gl, expg, maf, dist, labels, max_kb_dist=7, out_path=mine, n_threads=2)
+    assert sorted(ref.splitlines()) == sorted(open(mine, "rb").read().splitlines())
+    if threads == 1:
+        assert ref == open(mine, "rb").read()
+
+
+def test_survey_digests():
+    """Digests recorded independently in SURVEY.md App. D for the same generator + reference."""
+    fx = H.MANIFEST["fixtures"]
+    assert fx["p"]["variants"]["ext"]["md5"] == "f9c52f5e8dd422d542e9b55c0a5e2701"
+    assert fx["q"]["variants"]["ext"]["md5"] == "e141c2ae9780434e2bbe2ec6ef5ce977"
+    assert fx["edge"]["variants"]["ext"]["md5"] == "d6c15d75d16040b9c6e3cc0545e8f6d3"
+
+
+def test_preprocess_rejects_nan():
+    raw = np.full((2, 2, 3), 0.25)
+    raw[1, 1, 0] = np.nan
+    with pytest.raises(ValueError):
+        O.preprocess(raw)
