@@ -1,0 +1,159 @@
+/* ngsld_b200.h — C ABI of the B200-native pairwise-LD engine (libngsld_b200.so).
+ *
+ * Drop-in boundary for the pairwise-LD hot path of fgvieira/ngsLD 1.2.1.  The reference has no
+ * plugin/FFI layer; the path sits behind the per-first-site task `void calc_pair_LD(void*)`
+ * (reference ngsLD.hpp:58, body ngsLD.cpp:229-359) that `main` hands to the pthread pool with
+ * `threadpool_add` (reference shared/threadpool.h:139-140, call site ngsLD.cpp:169), and behind the
+ * numeric helpers that task calls (reference shared/gen_func.hpp:99-102, ngsLD.hpp:59).  Each entry
+ * point below names the reference interface it replaces.  INTEGRATION.md shows the few lines a
+ * maintainer of the reference would add to ngsLD.cpp to call this library instead of the pool.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer; device memory is
+ * owned by the context; every function returns 0 on success or a negative NGSLD_E_* code, with a
+ * message available from ngsld_last_error(); no C++ exception crosses this boundary; one host
+ * thread per context at a time; contexts on different GPUs are independent (multi-GPU = one context
+ * per device, first-site ranges from ngsld_partition()).  There is NO CPU fallback: without a CUDA
+ * device ngsld_create() fails with NGSLD_E_CUDA.
+ */
+#ifndef NGSLD_B200_H
+#define NGSLD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGSLD_ABI_VERSION 1
+
+/* error codes (the reference instead prints "ERROR: [func] msg" and exit(-1), shared/gen_func.cpp:12-18) */
+#define NGSLD_OK 0
+#define NGSLD_E_INVALID (-1) /* bad argument / call order                                  */
+#define NGSLD_E_CUDA (-2)    /* no device, or a CUDA runtime call failed                   */
+#define NGSLD_E_NOMEM (-3)   /* host or device allocation failed                           */
+#define NGSLD_E_DATA (-4)    /* input data rejected (NaN genotype, maf outside [0,1], bad positions) */
+#define NGSLD_E_SINK (-5)    /* the caller's sink returned non-zero                        */
+#define NGSLD_E_IO (-6)      /* file could not be read / parsed                            */
+
+typedef struct ngsld_ctx ngsld_ctx;
+
+/* One output row = one site pair.  Field order follows the reference's TSV columns
+ * (ngsLD.cpp:314-351): dist r2_ExpG D Dp r2 | sample_size maf1* maf2* hap00 hap01 hap10 hap11
+ * hap_maf1 hap_maf2 chi2 loglike* nIter   (* = not stored: maf1/maf2 are maf[s1]/maf[s2] and
+ * loglike is the literal 0.0, ngsLD.cpp:347). */
+typedef struct {
+  double dist;       /* accumulated pos_dist over (s1, s2], ngsLD.cpp:241; +inf across chromosomes */
+  double r2_expg;    /* pearson_r(), ngsLD.cpp:290,365-367 — bit-exact (x87 recurrence emulated)   */
+  double D, Dp, r2;  /* ngsLD.cpp:300,304,306                                                       */
+  double hap[4];     /* haplo_freq() output, shared/gen_func.cpp:1027-1059                          */
+  double hap_maf[2]; /* ngsLD.cpp:297-298                                                           */
+  float chi2;        /* float arithmetic as in ngsLD.cpp:328-333                                    */
+  uint32_t n_iter;   /* haplo_freq() return value: 0-based converging pass, 100 = not converged     */
+  uint32_t n_used;   /* individuals used by the EM (sample_size column)                             */
+  uint32_t s1, s2;   /* site indices                                                                */
+  uint32_t reserved;
+} ngsld_pair_row;    /* 112 bytes */
+
+/* The fields of the reference's `params` (ngsLD.hpp:11-44) that shape the pair scan, with the
+ * reference's defaults (parse_args.cpp:6-29) filled in by ngsld_scan_defaults(). */
+typedef struct {
+  uint64_t max_kb_dist;   /* 0 = unlimited; break when max_kb_dist*1000 < dist (ngsLD.cpp:252)   */
+  uint64_t max_snp_dist;  /* 0 = unlimited; break when max_snp_dist < s2-s1     (ngsLD.cpp:258)   */
+  double min_maf;         /* ngsLD.cpp:264,270                                                    */
+  double rnd_sample;      /* keep a candidate pair iff !(u > rnd_sample), ngsLD.cpp:277           */
+  uint64_t seed;          /* master gsl_rng_taus seed, ngsLD.cpp:70                               */
+  int ignore_miss_data;   /* shared/gen_func.cpp:1089                                             */
+  int extend_out;         /* only affects TSV text (ngsld_scan_tsv)                               */
+  int strict;             /* 1: EM in the reference's exact operation order (bit-identical hap/D/D'/r2,
+                             slower); 0: fast kernel, |delta| <= 1e-9 at equal nIter               */
+  int reserved;
+} ngsld_scan_params;
+
+/* Timing and work counters of the last scan on this context (device times from CUDA events on the
+ * context's own streams). */
+typedef struct {
+  uint64_t n_pairs;        /* rows produced                                           */
+  uint64_t sum_em_passes;  /* total EM passes executed (nIter+1, capped at 100)        */
+  uint64_t n_launches;     /* kernels launched by this library during the scan        */
+  double ms_em;            /* sum of EM-kernel durations                              */
+  double ms_pearson;       /* sum of r2_ExpG-kernel durations                         */
+  double ms_format;        /* sum of TSV-formatter durations                          */
+  double ms_device_total;  /* first launch -> last result byte in host memory          */
+  double ms_plan;          /* host planning (windows, sampling)                       */
+  uint64_t h2d_bytes, d2h_bytes;
+} ngsld_scan_stats;
+
+/* sinks: called on the scanning host thread, rows in (s1, s2) order — the order the reference
+ * produces with --n_threads 1 (FIFO pool, shared/threadpool.c:283-286).  Return non-zero to abort. */
+typedef int (*ngsld_row_sink)(void *user, const ngsld_pair_row *rows, uint64_t n_rows);
+typedef int (*ngsld_text_sink)(void *user, const char *bytes, uint64_t n_bytes, uint64_t n_rows);
+
+/* ---- context --------------------------------------------------------------------------------- */
+int ngsld_abi_version(void);
+/* replaces threadpool_create() (shared/threadpool.c:51-99, call site ngsLD.cpp:154): binds a GPU. */
+int ngsld_create(ngsld_ctx **out, int device);
+/* replaces threadpool_destroy() + the free_ptr block (ngsLD.cpp:197-216). */
+void ngsld_destroy(ngsld_ctx *ctx);
+/* message for the last failure on ctx (ctx == NULL: last ngsld_create failure of this thread). */
+const char *ngsld_last_error(const ngsld_ctx *ctx);
+/* Optional: run all device work of this context on a caller-provided cudaStream_t (e.g. the
+ * framework's current stream) instead of the context's own; NULL restores the default. */
+int ngsld_set_stream(ngsld_ctx *ctx, void *cuda_stream);
+/* cap on rows per device chunk (0 = default); result buffers scale with it. */
+int ngsld_set_chunk_rows(ngsld_ctx *ctx, uint64_t rows);
+
+/* ---- per-site preparation (host, bit-identical to the reference's glibc path) ---------------- */
+/* replaces the per-cell math of read_geno()'s binary branch (shared/read_data.cpp:28-46), the optional
+ * call_geno() pass (ngsLD.cpp:92-98), est_maf() (ngsLD.cpp:103-104, shared/gen_func.cpp:974-1009) and
+ * the conv_space/expected-genotype loop (ngsLD.cpp:107-114).  raw = the file's doubles
+ * [n_sites][n_ind][3]; outputs gl [n_sites][n_ind][3] (normal space), expg [n_sites][n_ind], maf
+ * [n_sites].  from_log_cells = 1: `raw` already holds log-space cells (text input path). */
+int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int log_scale, int from_log_cells,
+                        int ignore_miss_data, int call_geno, double N_thresh, double call_thresh, int n_threads,
+                        double *gl, double *expg, double *maf);
+
+/* ---- data upload ----------------------------------------------------------------------------- */
+/* replaces the shared read-only arrays of `params` (geno_lkl, expected_geno, maf; ngsLD.hpp:36-41):
+ * copies them to the device (and derives the per-site x87 Pearson terms on the host FPU). */
+int ngsld_set_sites(ngsld_ctx *ctx, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
+                    uint64_t n_ind);
+/* replaces params.pos_dist / params.labels (ngsLD.cpp:119-135).  pos_dist NULL = all +inf (no --pos);
+ * labels NULL = "(null)" like the reference prints.  labels are only used by ngsld_scan_tsv. */
+int ngsld_set_positions(ngsld_ctx *ctx, const double *pos_dist, const char *const *labels);
+
+/* ---- the scan: replaces the threadpool_add(calc_pair_LD) fan-out + threadpool_wait ------------ */
+void ngsld_scan_defaults(ngsld_scan_params *p);
+/* Planning only: number of rows first sites [s1_lo, s1_hi) will produce. */
+int ngsld_scan_count(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, uint64_t *n_rows);
+/* Equal-row-count first-site ranges for n_parts workers: bounds[0..n_parts], bounds[0]=0, bounds[n_parts]=n_sites. */
+int ngsld_partition(ngsld_ctx *ctx, const ngsld_scan_params *p, int n_parts, uint64_t *bounds);
+/* Binary rows to a sink. */
+int ngsld_scan(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_row_sink sink,
+               void *user);
+/* Binary rows into one caller buffer of `cap` rows (fails with NGSLD_E_INVALID if it does not fit). */
+int ngsld_scan_into(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p,
+                    ngsld_pair_row *out, uint64_t cap, uint64_t *n_rows);
+/* TSV bytes exactly as the reference's fprintf block (ngsLD.cpp:314-351), formatted on the device. */
+int ngsld_scan_tsv(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_text_sink sink,
+                   void *user);
+/* Same work with results left in device memory (no D2H): the HBM-resident timing leg of bench.py. */
+int ngsld_scan_device(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p);
+int ngsld_get_stats(const ngsld_ctx *ctx, ngsld_scan_stats *out);
+
+/* ---- explicit pairs: replaces direct calls of haplo_freq()/pearson_r() (gen_func.hpp:101, ngsLD.hpp:59) */
+int ngsld_pairs(ngsld_ctx *ctx, const uint32_t *s1, const uint32_t *s2, uint64_t n_pairs, int ignore_miss_data,
+                int strict, ngsld_pair_row *out);
+
+/* ---- pieces exposed for tests / callers that plan themselves --------------------------------- */
+/* replaces the per-site generator seeding loop (ngsLD.cpp:165-166). */
+int ngsld_site_seeds(uint64_t seed, uint64_t n_sites, uint64_t *out);
+/* header line (ngsLD.cpp:77); returns bytes written (excluding NUL) or negative. */
+int ngsld_tsv_header(int extend_out, char *buf, size_t cap);
+/* FP64 FMA issue-rate probe (GFLOP/s, 2 flop per FMA) — the roofline that actually binds this path. */
+int ngsld_probe_fp64(ngsld_ctx *ctx, double *gflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSLD_B200_H */

@@ -1,0 +1,217 @@
+// Everything on the path that is not the fast EM: the bit-faithful EM, the x87-exact r2_ExpG,
+// window -> pair-list expansion, per-site taus sampling, and an FP64 issue-rate probe.
+#include "aux_kernels.cuh"
+#include "fp80.cuh"
+
+namespace aux {
+
+// ------------------------------------------------------------------------------------------------
+// Bit-faithful EM: one thread per pair, individuals in order, every operation individually rounded
+// in the reference's association order (shared/gen_func.cpp:1076-1119, 1027-1059).  Rounding-
+// preserving hoists only: P[k][h] = f[k]*f[h] per pass, L[a][b] = p1[a]*p2[b] per individual (the
+// reference's bracket p*q + p*q is exactly 2L).  The `sum` terms keep ((f_k f_h) p1) p2.
+__global__ void __launch_bounds__(128) em_strict_kernel(SiteTable T, PairChunk C, int ignore_miss, DevCounters *ctr) {
+  const size_t row_doubles = (size_t)T.n_pad * 3;
+  unsigned long long passes = 0;
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < C.n_pairs;
+       p += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t s1 = C.s1[p], s2 = C.s2[p];
+    const double *ga = T.gl + (size_t)s1 * row_doubles, *gb = T.gl + (size_t)s2 * row_doubles;
+    const double m1 = T.maf[s1], m2 = T.maf[s2];
+    double f[4];
+    f[0] = __dmul_rn(__dsub_rn(1.0, m1), __dsub_rn(1.0, m2));
+    f[1] = __dmul_rn(__dsub_rn(1.0, m1), m2);
+    f[2] = __dmul_rn(m1, __dsub_rn(1.0, m2));
+    f[3] = __dmul_rn(m1, m2);
+    uint32_t it, used = 0;
+    for (it = 0; it < NGSLD_ITER_MAX; it++) {
+      double P[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int h = 0; h < 4; h++) P[k][h] = __dmul_rn(f[k], f[h]);
+      double acc[4] = {0, 0, 0, 0};
+      used = 0;
+      for (uint32_t i = 0; i < T.n_ind; i++) {
+        double pa[3], pb[3];
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          pa[g] = ga[3 * (size_t)i + g];
+          pb[g] = gb[3 * (size_t)i + g];
+        }
+        if (ignore_miss && (gl_missing(pa[0], pa[1], pa[2]) || gl_missing(pb[0], pb[1], pb[2]))) continue;
+        used++;
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int h = 0; h < 4; h++) {
+            const int a = (k >> 1) + (h >> 1), b = (k & 1) + (h & 1);
+            tot = __dadd_rn(tot, __dmul_rn(__dmul_rn(P[k][h], pa[a]), pb[b]));
+          }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double part = 0.0;
+#pragma unroll
+          for (int h = 0; h < 4; h++) {
+            const int a = (k >> 1) + (h >> 1), b = (k & 1) + (h & 1);
+            const double l = __dmul_rn(pa[a], pb[b]);
+            part = __dadd_rn(part, __dmul_rn(P[k][h], __dadd_rn(l, l)));
+          }
+          acc[k] = __dadd_rn(acc[k], __ddiv_rn(part, tot));
+        }
+      }
+      const double prev[4] = {f[0], f[1], f[2], f[3]};
+      const double two_x = (double)(2ull * used);
+#pragma unroll
+      for (int k = 0; k < 4; k++) f[k] = __ddiv_rn(acc[k], two_x);
+#pragma unroll
+      for (int k = 0; k < 4; k++)  // sequential: later entries see the already-updated earlier ones
+        f[k] = __ddiv_rn(f[k], __dadd_rn(__dadd_rn(__dadd_rn(f[0], f[1]), f[2]), f[3]));
+      double eps = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double d = fabs(__dsub_rn(f[k], prev[k]));
+        if (d > eps) eps = d;
+      }
+      if (eps < NGSLD_EPS) break;
+    }
+    passes += it < NGSLD_ITER_MAX ? it + 1 : NGSLD_ITER_MAX;
+    derive_and_store(C.rows + p, f, it, used);
+  }
+  // warp-aggregate the pass counter
+  for (int o = 16; o > 0; o >>= 1) passes += __shfl_xor_sync(0xffffffffu, passes, o);
+  if ((threadIdx.x & 31) == 0 && passes) atomicAdd(&ctr->em_passes, passes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// r2_ExpG: the pair-dependent part of gsl_stats_correlation's recurrence (reference ngsLD.cpp:365-367;
+// GSL statistics/covariance_source.c) in emulated x87 arithmetic.  Per site the host FPU already
+// produced delta_i = x_i - mean_(i-1) (80-bit) and q = sqrt((double)sum_sq); here
+//     sum_cross = sum_{i>=1} fl80( fl80(da_i * db_i) * (long double)(i/(i+1.0)) )   (in order)
+//     r = fl80( sum_cross / (long double)(qa*qb) ),  r2 = (double)r * (double)r.
+// One thread per pair; the sum is inherently sequential.
+__global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C) {
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < C.n_pairs;
+       p += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t s1 = C.s1[p], s2 = C.s2[p];
+    const uint64_t *ma = T.dx_sig + (size_t)s1 * T.n_pad, *mb = T.dx_sig + (size_t)s2 * T.n_pad;
+    const uint16_t *ea = T.dx_se + (size_t)s1 * T.n_pad, *eb = T.dx_se + (size_t)s2 * T.n_pad;
+    x87::ext acc = x87::zero(0);
+    for (uint32_t i = 1; i < T.n_ind; i++) {
+      const x87::ext da = x87::from_bits(ma[i], ea[i]);
+      const x87::ext db = x87::from_bits(mb[i], eb[i]);
+      const x87::ext ratio = x87::from_double(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0)));
+      acc = x87::add(acc, x87::mul(x87::mul(da, db), ratio));
+    }
+    const double den = __dmul_rn(T.q[s1], T.q[s2]);
+    double r;
+    if (den == 0.0 || den != den) {
+      // x87: 0/0 -> default NaN; finite/0 -> signed infinity
+      if (acc.sig == 0 || den != den)
+        r = __longlong_as_double(0xfff8000000000000ll);
+      else
+        r = __longlong_as_double(acc.neg ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
+    } else {
+      r = x87::to_double(x87::div(acc, x87::from_double(den)));
+    }
+    C.rows[p].r2_expg = __dmul_rn(r, r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window plan -> explicit pair list for output rows [row_lo, row_lo + n): row g belongs to the
+// compact first site c1 with row_off[c1] <= g < row_off[c1+1]; its partner is c1 + 1 + (g - row_off[c1]).
+__global__ void expand_window_kernel(const unsigned long long *row_off, const uint32_t *cs, uint32_t n_compact,
+                                     unsigned long long row_lo, unsigned long long n, uint32_t *s1, uint32_t *s2) {
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
+       p += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long g = row_lo + p;
+    uint32_t lo = 0, hi = n_compact;  // largest c with row_off[c] <= g
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (row_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t c1 = lo, c2 = c1 + 1 + (uint32_t)(g - row_off[c1]);
+    s1[p] = cs ? cs[c1] : c1;
+    s2[p] = cs ? cs[c2] : c2;
+  }
+}
+
+// site indices + accumulated distance (reference ngsLD.cpp:241) into the output rows
+__global__ void fill_rows_kernel(SiteTable T, PairChunk C) {
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < C.n_pairs;
+       p += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t a = C.s1[p], b = C.s2[p];
+    double dist = __longlong_as_double(0x7ff0000000000000ll);
+    if (T.cum != nullptr && T.seg[a] == T.seg[b]) dist = T.cum[b] - T.cum[a];
+    ngsld_pair_row *r = C.rows + p;
+    r->dist = dist;
+    r->s1 = a;
+    r->s2 = b;
+    r->reserved = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Random pair sampling (reference ngsLD.cpp:277 with the per-site gsl_rng_taus of ngsLD.cpp:165-166;
+// generator restated from GSL rng/taus.c).  One thread walks one first site's candidate stream.
+struct Taus {
+  uint32_t a, b, c;
+  __device__ __forceinline__ uint32_t get() {
+    a = ((a & 4294967294u) << 12) ^ (((a << 13) ^ a) >> 19);
+    b = ((b & 4294967288u) << 4) ^ (((b << 2) ^ b) >> 25);
+    c = ((c & 4294967280u) << 17) ^ (((c << 3) ^ c) >> 11);
+    return a ^ b ^ c;
+  }
+  __device__ __forceinline__ void set(unsigned long long seed) {
+    if (seed == 0) seed = 1;
+    a = (uint32_t)(69069ull * seed);
+    b = (uint32_t)(69069ull * a);
+    c = (uint32_t)(69069ull * b);
+    for (int k = 0; k < 6; k++) get();
+  }
+};
+
+// mode 0: counts[c1 - c_lo] = kept pairs; mode 1: write the kept partners at row_off[c1] - row_base.
+__global__ void taus_sample_kernel(const unsigned long long *site_seeds, const uint32_t *cs, const uint32_t *cw_end,
+                                   uint32_t c_lo, uint32_t c_hi, double rnd_sample, int mode,
+                                   unsigned long long *counts, const unsigned long long *row_off,
+                                   unsigned long long row_base, unsigned long long row_cap, uint32_t *s1,
+                                   uint32_t *s2) {
+  for (uint32_t c1 = c_lo + blockIdx.x * blockDim.x + threadIdx.x; c1 < c_hi; c1 += gridDim.x * blockDim.x) {
+    const uint32_t site = cs ? cs[c1] : c1;
+    Taus g;
+    g.set(site_seeds[site]);
+    unsigned long long kept = 0;
+    const unsigned long long base = mode ? row_off[c1] - row_base : 0;
+    for (uint32_t c2 = c1 + 1; c2 < cw_end[c1]; c2++) {
+      const double u = __dmul_rn(__ddiv_rn((double)g.get(), 4294967296.0), 1.0);
+      if (u > rnd_sample) continue;
+      if (mode) {
+        const unsigned long long o = base + kept;
+        if (o < row_cap) {
+          s1[o] = site;
+          s2[o] = cs ? cs[c2] : c2;
+        }
+      }
+      kept++;
+    }
+    if (!mode) counts[c1 - c_lo] = kept;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA issue-rate probe: 8 independent chains per thread.
+__global__ void fp64_probe_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace aux

@@ -1,0 +1,17 @@
+// Declarations of the non-EM-fast kernels (definitions in aux_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace aux {
+__global__ void em_strict_kernel(SiteTable T, PairChunk C, int ignore_miss, DevCounters *ctr);
+__global__ void pearson_kernel(SiteTable T, PairChunk C);
+__global__ void expand_window_kernel(const unsigned long long *row_off, const uint32_t *cs, uint32_t n_compact,
+                                     unsigned long long row_lo, unsigned long long n, uint32_t *s1, uint32_t *s2);
+__global__ void fill_rows_kernel(SiteTable T, PairChunk C);
+__global__ void taus_sample_kernel(const unsigned long long *site_seeds, const uint32_t *cs, const uint32_t *cw_end,
+                                   uint32_t c_lo, uint32_t c_hi, double rnd_sample, int mode,
+                                   unsigned long long *counts, const unsigned long long *row_off,
+                                   unsigned long long row_base, unsigned long long row_cap, uint32_t *s1,
+                                   uint32_t *s2);
+__global__ void fp64_probe_kernel(double *out, int iters);
+}  // namespace aux

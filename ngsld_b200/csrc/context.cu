@@ -1,0 +1,1068 @@
+// C-ABI layer of libngsld_b200.so: context, uploads, scan planner and chunked scan driver.
+// See include/ngsld_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "em_kernels.cuh"
+#include "format.cuh"
+#include "host_prep.h"
+
+namespace emfast {
+#define DECL_LPG(n)                              \
+  extern const EmVariant em_variants_lpg##n[];   \
+  extern const int em_variants_lpg##n##_count;
+DECL_LPG(4) DECL_LPG(8) DECL_LPG(16) DECL_LPG(32) DECL_LPG(64) DECL_LPG(128) DECL_LPG(256)
+#undef DECL_LPG
+}  // namespace emfast
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct ChunkBuf {
+  uint32_t *d_s1 = nullptr, *d_s2 = nullptr;
+  ngsld_pair_row *d_rows = nullptr;
+  ngsld_pair_row *h_rows = nullptr;  // pinned
+  char *d_text = nullptr;            // formatted TSV bytes (slots, then compacted)
+  char *d_text_out = nullptr;
+  char *h_text = nullptr;            // pinned
+  unsigned long long *d_line_off = nullptr;
+  unsigned long long *h_text_len = nullptr;  // pinned: {bytes, overflow flag}
+  cudaEvent_t ev_ready = nullptr, ev_em0 = nullptr, ev_em1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr,
+              ev_f0 = nullptr, ev_f1 = nullptr, ev_done = nullptr;
+  uint64_t n_rows = 0;
+  bool pending = false;
+};
+
+struct Plan {
+  std::vector<uint32_t> cs;                  // compact index -> site
+  std::vector<uint32_t> cw_end;              // per compact first site: exclusive partner end (compact)
+  std::vector<unsigned long long> row_off;   // nC + 1 prefix of rows per compact first site
+  uint32_t n_compact = 0, c_lo = 0, c_hi = 0;
+  bool identity = true, sampled = false;
+  unsigned long long total = 0;
+};
+
+enum ScanMode { MODE_ROWS, MODE_TEXT, MODE_DEVICE };
+
+}  // namespace
+
+struct ngsld_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int smem_optin = 0;
+  cudaStream_t own_main = nullptr, s_main = nullptr, s_aux = nullptr, s_copy = nullptr;
+  std::string err;
+  // sites
+  uint64_t n_sites = 0, n_ind = 0, n_pad = 0;
+  double *d_gl = nullptr, *d_maf = nullptr, *d_q = nullptr;
+  uint64_t *d_dx_sig = nullptr;
+  uint16_t *d_dx_se = nullptr;
+  std::vector<double> h_maf;
+  // positions / labels
+  bool have_pos = false;
+  std::vector<double> h_cum;
+  std::vector<uint32_t> h_seg;
+  double *d_cum = nullptr;
+  uint32_t *d_seg = nullptr;
+  bool have_labels = false;
+  std::vector<std::string> h_labels;
+  char *d_label_blob = nullptr;
+  uint32_t *d_label_off = nullptr;  // n_sites + 1
+  uint32_t max_label_len = 6;       // "(null)"
+  // plan buffers
+  uint32_t *d_cs = nullptr, *d_cw_end = nullptr;
+  unsigned long long *d_row_off = nullptr, *d_seeds = nullptr, *d_counts = nullptr;
+  uint2 *d_tiles = nullptr;
+  size_t cap_compact = 0, cap_tiles = 0;
+  DevCounters *d_ctr = nullptr;
+  // chunks
+  uint64_t chunk_rows = 4ull << 20;
+  uint64_t alloc_rows = 0;
+  bool alloc_text = false, alloc_host = false;
+  ChunkBuf buf[2];
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  ngsld_scan_stats stats;
+  ngsld_ctx() { memset(&stats, 0, sizeof stats); }
+};
+
+namespace {
+
+int fail(ngsld_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? NGSLD_E_NOMEM : NGSLD_E_CUDA,              \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                              \
+  } while (0)
+
+template <class T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_chunks(ngsld_ctx *c) {
+  for (auto &b : c->buf) {
+    dfree(b.d_s1);
+    dfree(b.d_s2);
+    dfree(b.d_rows);
+    dfree(b.d_text);
+    dfree(b.d_text_out);
+    dfree(b.d_line_off);
+    if (b.h_rows) cudaFreeHost(b.h_rows);
+    if (b.h_text) cudaFreeHost(b.h_text);
+    if (b.h_text_len) cudaFreeHost(b.h_text_len);
+    b.h_rows = nullptr;
+    b.h_text = nullptr;
+    b.h_text_len = nullptr;
+  }
+  c->alloc_rows = 0;
+  c->alloc_text = c->alloc_host = false;
+}
+
+int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, uint32_t slot) {
+  if (rows < 1) rows = 1;
+  if (c->alloc_rows >= rows && (!need_host || c->alloc_host) && (!need_text || c->alloc_text)) return NGSLD_OK;
+  free_chunks(c);
+  for (auto &b : c->buf) {
+    CUDA_TRY(c, cudaMalloc(&b.d_s1, rows * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&b.d_s2, rows * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&b.d_rows, rows * sizeof(ngsld_pair_row)));
+    if (need_host && !need_text) CUDA_TRY(c, cudaMallocHost(&b.h_rows, rows * sizeof(ngsld_pair_row)));
+    if (need_text) {
+      CUDA_TRY(c, cudaMalloc(&b.d_text, rows * (size_t)slot));
+      CUDA_TRY(c, cudaMalloc(&b.d_text_out, rows * (size_t)slot));
+      CUDA_TRY(c, cudaMalloc(&b.d_line_off, (rows + rows / 1024 + 8) * sizeof(unsigned long long)));
+      CUDA_TRY(c, cudaMallocHost(&b.h_text, rows * (size_t)slot));
+      CUDA_TRY(c, cudaMallocHost(&b.h_text_len, 2 * sizeof(unsigned long long)));
+      CUDA_TRY(c, cudaMallocHost(&b.h_rows, rows * sizeof(ngsld_pair_row)));  // host-format fallback
+    }
+  }
+  c->alloc_rows = rows;
+  c->alloc_host = need_host && !need_text;
+  c->alloc_text = need_text;
+  return NGSLD_OK;
+}
+
+SiteTable site_table(const ngsld_ctx *c) {
+  SiteTable T;
+  T.gl = c->d_gl;
+  T.maf = c->d_maf;
+  T.dx_sig = c->d_dx_sig;
+  T.dx_se = c->d_dx_se;
+  T.q = c->d_q;
+  T.cum = c->have_pos ? c->d_cum : nullptr;
+  T.seg = c->d_seg;
+  T.n_sites = (uint32_t)c->n_sites;
+  T.n_ind = (uint32_t)c->n_ind;
+  T.n_pad = (uint32_t)c->n_pad;
+  return T;
+}
+
+// (IPL, LPG) for a sample size: the smallest group whose lanes hold <= 8 individuals each.
+const emfast::EmVariant *pick_variant(uint64_t n_ind) {
+  using namespace emfast;
+  struct Tab { const EmVariant *v; int n; } tabs[] = {
+      {em_variants_lpg4, em_variants_lpg4_count},     {em_variants_lpg8, em_variants_lpg8_count},
+      {em_variants_lpg16, em_variants_lpg16_count},   {em_variants_lpg32, em_variants_lpg32_count},
+      {em_variants_lpg64, em_variants_lpg64_count},   {em_variants_lpg128, em_variants_lpg128_count},
+      {em_variants_lpg256, em_variants_lpg256_count}};
+  const char *force = getenv("NGSLD_EM_VARIANT");  // "ipl,lpg" for experiments
+  int fi = 0, fl = 0;
+  if (force && sscanf(force, "%d,%d", &fi, &fl) == 2) {
+    for (auto &t : tabs)
+      for (int k = 0; k < t.n; k++)
+        if (t.v[k].ipl == fi && t.v[k].lpg == fl && (uint64_t)fi * fl >= n_ind) return &t.v[k];
+  }
+  for (auto &t : tabs) {
+    const int lpg = t.v[0].lpg;
+    const uint64_t ipl = (n_ind + lpg - 1) / lpg;
+    if (ipl > 8) continue;
+    for (int k = 0; k < t.n; k++)
+      if ((uint64_t)t.v[k].ipl >= ipl) return &t.v[k];
+  }
+  return nullptr;
+}
+
+// ---- planning -----------------------------------------------------------------------------------
+// Reproduces the control flow of calc_pair_LD's scan (reference ngsLD.cpp:240-282) as index ranges.
+int make_plan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params &P, Plan &pl) {
+  const uint64_t n = c->n_sites;
+  if (s1_hi > n) s1_hi = n;
+  if (s1_lo > s1_hi) s1_lo = s1_hi;
+  const std::vector<double> &maf = c->h_maf;
+  // sites that may appear in a pair at all: !(maf < min_maf)  (ngsLD.cpp:264,270)
+  std::vector<uint32_t> kp(n + 1);
+  pl.cs.clear();
+  pl.cs.reserve(n);
+  pl.identity = true;
+  for (uint64_t s = 0; s < n; s++) {
+    kp[s] = (uint32_t)pl.cs.size();
+    if (maf[s] < P.min_maf)
+      pl.identity = false;
+    else
+      pl.cs.push_back((uint32_t)s);
+  }
+  kp[n] = (uint32_t)pl.cs.size();
+  pl.n_compact = (uint32_t)pl.cs.size();
+  pl.c_lo = kp[s1_lo];
+  pl.c_hi = kp[s1_hi];
+  pl.cw_end.assign(pl.n_compact, 0);
+  // window end per first site (two-pointer; both break conditions are monotone in s1)
+  const double kb_limit = (double)(P.max_kb_dist * 1000ull);
+  uint64_t e = 0;
+  for (uint64_t s1 = 0; s1 < n; s1++) {
+    if (e < s1 + 1) e = s1 + 1;
+    while (e < n) {
+      double dist = INFINITY;
+      if (c->have_pos && c->h_seg[s1] == c->h_seg[e]) dist = c->h_cum[e] - c->h_cum[s1];
+      if (P.max_kb_dist > 0 && kb_limit < dist) break;            // ngsLD.cpp:252
+      if (P.max_snp_dist > 0 && P.max_snp_dist < e - s1) break;   // ngsLD.cpp:258
+      e++;
+    }
+    if (!(maf[s1] < P.min_maf)) pl.cw_end[kp[s1]] = kp[e];
+  }
+  pl.sampled = P.rnd_sample < 1.0;
+  pl.row_off.assign((size_t)pl.n_compact + 1, 0);
+  if (!pl.sampled) {
+    unsigned long long acc = 0;
+    for (uint32_t k = 0; k < pl.n_compact; k++) {
+      pl.row_off[k] = acc;
+      if (k >= pl.c_lo && k < pl.c_hi && pl.cw_end[k] > k + 1) acc += pl.cw_end[k] - k - 1;
+    }
+    pl.row_off[pl.n_compact] = acc;
+    pl.total = acc;
+  }
+  return NGSLD_OK;
+}
+
+int ensure_plan_buffers(ngsld_ctx *c, size_t n_compact) {
+  if (c->cap_compact >= n_compact + 1) return NGSLD_OK;
+  dfree(c->d_cs);
+  dfree(c->d_cw_end);
+  dfree(c->d_row_off);
+  dfree(c->d_counts);
+  const size_t cap = n_compact + 1;
+  CUDA_TRY(c, cudaMalloc(&c->d_cs, cap * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_cw_end, cap * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_row_off, cap * sizeof(unsigned long long)));
+  CUDA_TRY(c, cudaMalloc(&c->d_counts, cap * sizeof(unsigned long long)));
+  c->cap_compact = cap;
+  return NGSLD_OK;
+}
+
+int upload_plan(ngsld_ctx *c, Plan &pl, const ngsld_scan_params &P) {
+  int rc = ensure_plan_buffers(c, pl.n_compact);
+  if (rc) return rc;
+  if (pl.n_compact) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_cs, pl.cs.data(), pl.n_compact * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_cw_end, pl.cw_end.data(), pl.n_compact * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_main));
+  }
+  c->stats.h2d_bytes += (uint64_t)pl.n_compact * 8;
+  if (pl.sampled) {
+    // per-site generator seeds from the master stream (host, serial as in the reference), then the
+    // per-first-site kept-pair counts on the device
+    std::vector<uint64_t> seeds(c->n_sites);
+    hostprep::site_seeds(P.seed, c->n_sites, seeds.data());
+    dfree(c->d_seeds);
+    CUDA_TRY(c, cudaMalloc(&c->d_seeds, c->n_sites * sizeof(unsigned long long)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_seeds, seeds.data(), c->n_sites * 8, cudaMemcpyHostToDevice, c->s_main));
+    c->stats.h2d_bytes += c->n_sites * 8;
+    const uint32_t span = pl.c_hi - pl.c_lo;
+    std::vector<unsigned long long> counts(span);
+    if (span) {
+      const int threads = 128;
+      const unsigned blocks = (unsigned)std::min<uint64_t>((span + threads - 1) / threads, 65535u * 16u);
+      aux::taus_sample_kernel<<<blocks, threads, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end,
+                                                                 pl.c_lo, pl.c_hi, P.rnd_sample, 0, c->d_counts, nullptr, 0,
+                                                                 0, nullptr, nullptr);
+      c->stats.n_launches++;
+      CUDA_TRY(c, cudaGetLastError());
+      CUDA_TRY(c, cudaMemcpyAsync(counts.data(), c->d_counts, span * 8ull, cudaMemcpyDeviceToHost, c->s_main));
+      CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+      c->stats.d2h_bytes += span * 8ull;
+    }
+    unsigned long long acc = 0;
+    for (uint32_t k = 0; k < pl.n_compact; k++) {
+      pl.row_off[k] = acc;
+      if (k >= pl.c_lo && k < pl.c_hi) acc += counts[k - pl.c_lo];
+    }
+    pl.row_off[pl.n_compact] = acc;
+    pl.total = acc;
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_row_off, pl.row_off.data(), ((size_t)pl.n_compact + 1) * 8, cudaMemcpyHostToDevice, c->s_main));
+  c->stats.h2d_bytes += ((uint64_t)pl.n_compact + 1) * 8;
+  // the host vectors must outlive the async copies
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  return NGSLD_OK;
+}
+
+// first compact site owning global row g
+uint32_t row_owner(const Plan &pl, unsigned long long g) {
+  auto it = std::upper_bound(pl.row_off.begin(), pl.row_off.begin() + pl.n_compact, g);
+  return (uint32_t)(it - pl.row_off.begin()) - 1;
+}
+
+struct EmChoice {
+  const emfast::EmVariant *v = nullptr;
+  bool tile = false;
+  uint32_t TA = 0, TB = 0;
+  size_t dyn_smem = 0;
+  int blocks_list = 0, blocks_tile = 0;
+};
+
+int choose_em(ngsld_ctx *c, const Plan &pl, EmChoice &ch) {
+  ch.v = pick_variant(c->n_ind);
+  if (!ch.v) return NGSLD_OK;  // falls back to the strict kernel (n_ind > 2048)
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->list_fn, emfast::CTA_THREADS, 0));
+  ch.blocks_list = std::max(1, occ) * c->sm_count;
+  const size_t row_bytes = c->n_pad * 24;
+  const size_t budget = (size_t)c->smem_optin - 4096;
+  uint32_t rows_fit = (uint32_t)std::min<size_t>(budget / row_bytes, 64);
+  uint32_t t = rows_fit / 2;
+  if (t > 32) t = 32;
+  const char *path = getenv("NGSLD_EM_PATH");  // "list" | "tile" for experiments
+  const char *tdim = getenv("NGSLD_TILE");
+  if (tdim && atoi(tdim) > 0 && (uint32_t)atoi(tdim) <= t) t = atoi(tdim);
+  ch.tile = !pl.sampled && t >= 4;
+  if (path && !strcmp(path, "list")) ch.tile = false;
+  if (path && !strcmp(path, "tile") && !pl.sampled && t >= 1) ch.tile = true;
+  if (ch.tile) {
+    ch.TA = ch.TB = t;
+    ch.dyn_smem = (size_t)(ch.TA + ch.TB) * row_bytes;
+    CUDA_TRY(c, cudaFuncSetAttribute(ch.v->tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.dyn_smem));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->tile_fn, emfast::CTA_THREADS, ch.dyn_smem));
+    ch.blocks_tile = std::max(1, occ) * c->sm_count;
+  }
+  return NGSLD_OK;
+}
+
+// Tiles covering the pairs of compact first sites [ca, cb): A-blocks of TA first sites from ca, each
+// crossed with TB-wide partner blocks up to the block's furthest window end.  block_off[k] = index of
+// the first tile of A-block k (block_off.back() = tiles.size()).
+void build_tiles(const Plan &pl, uint32_t ca, uint32_t cb, uint32_t TA, uint32_t TB, std::vector<uint2> &tiles,
+                 std::vector<size_t> &block_off) {
+  tiles.clear();
+  block_off.clear();
+  for (uint32_t a = ca; a < cb; a += TA) {
+    block_off.push_back(tiles.size());
+    const uint32_t a_last = std::min(cb, a + TA) - 1;
+    const uint32_t bmax = pl.cw_end[a_last];  // cw_end is non-decreasing over first sites
+    for (uint32_t b = a + 1; b < bmax; b += TB) tiles.push_back(make_uint2(a, b));
+  }
+  block_off.push_back(tiles.size());
+}
+
+int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const EmChoice &ch, ChunkBuf &b,
+                 unsigned long long r0, unsigned long long r1, size_t t0, size_t t1, ScanMode mode,
+                 const fmt::FormatArgs *fa) {
+  const unsigned long long n = r1 - r0;
+  const SiteTable T = site_table(c);
+  PairChunk C;
+  C.s1 = b.d_s1;
+  C.s2 = b.d_s2;
+  C.rows = b.d_rows;
+  C.n_pairs = n;
+  const int threads = 256;
+  const unsigned gblocks = (unsigned)std::min<unsigned long long>((n + threads - 1) / threads, (unsigned long long)c->sm_count * 32);
+  const uint32_t ca = row_owner(pl, r0), cb = row_owner(pl, r1 - 1) + 1;
+  if (pl.sampled) {
+    const uint32_t span = cb - ca;
+    const unsigned sb = (unsigned)std::min<uint64_t>((span + 127) / 128, 65535u * 16u);
+    aux::taus_sample_kernel<<<sb, 128, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end, ca, cb,
+                                                       P.rnd_sample, 1, nullptr, c->d_row_off, r0, n, b.d_s1, b.d_s2);
+  } else {
+    aux::expand_window_kernel<<<gblocks, threads, 0, c->s_main>>>(c->d_row_off, pl.identity ? nullptr : c->d_cs,
+                                                                   pl.n_compact, r0, n, b.d_s1, b.d_s2);
+  }
+  aux::fill_rows_kernel<<<gblocks, threads, 0, c->s_main>>>(T, C);
+  c->stats.n_launches += 2;
+  CUDA_TRY(c, cudaEventRecord(b.ev_ready, c->s_main));
+  // r2_ExpG on the auxiliary stream, concurrently with the EM
+  CUDA_TRY(c, cudaStreamWaitEvent(c->s_aux, b.ev_ready, 0));
+  CUDA_TRY(c, cudaEventRecord(b.ev_p0, c->s_aux));
+  {
+    const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
+    aux::pearson_kernel<<<pb, 128, 0, c->s_aux>>>(T, C);
+    c->stats.n_launches++;
+  }
+  CUDA_TRY(c, cudaEventRecord(b.ev_p1, c->s_aux));
+  // EM
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
+  CUDA_TRY(c, cudaEventRecord(b.ev_em0, c->s_main));
+  if (P.strict || ch.v == nullptr) {
+    const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
+    aux::em_strict_kernel<<<sb, 128, 0, c->s_main>>>(T, C, P.ignore_miss_data, c->d_ctr);
+  } else if (ch.tile) {
+    emfast::TileArgs A;
+    A.tiles = c->d_tiles + t0;
+    A.n_tiles = t1 - t0;
+    A.cs = pl.identity ? nullptr : c->d_cs;
+    A.cw_end = c->d_cw_end;
+    A.row_off = c->d_row_off;
+    A.row_lo = r0;
+    A.row_hi = r1;
+    A.n_compact = pl.n_compact;
+    A.TA = ch.TA;
+    A.TB = ch.TB;
+    int ign = P.ignore_miss_data;
+    ngsld_pair_row *rows = b.d_rows;
+    SiteTable Tt = T;
+    DevCounters *ctr = c->d_ctr;
+    void *args[] = {&Tt, &rows, &A, &ign, &ctr};
+    const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<size_t>(t1 - t0, 1), ch.blocks_tile);
+    CUDA_TRY(c, cudaLaunchKernel(ch.v->tile_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, ch.dyn_smem, c->s_main));
+  } else {
+    int ign = P.ignore_miss_data;
+    SiteTable Tt = T;
+    PairChunk Cc = C;
+    DevCounters *ctr = c->d_ctr;
+    void *args[] = {&Tt, &Cc, &ign, &ctr};
+    const unsigned long long groups_per_cta = emfast::CTA_THREADS / ch.v->lpg;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((n + groups_per_cta - 1) / groups_per_cta, ch.blocks_list);
+    CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, 0, c->s_main));
+  }
+  c->stats.n_launches++;
+  CUDA_TRY(c, cudaEventRecord(b.ev_em1, c->s_main));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->s_main, b.ev_p1, 0));
+  if (mode == MODE_TEXT) {
+    CUDA_TRY(c, cudaEventRecord(b.ev_f0, c->s_main));
+    int rc = fmt::launch_format(*fa, T, b.d_rows, n, b.d_text, b.d_line_off, b.d_text_out, c->sm_count, c->s_main);
+    if (rc < 0) return fail(c, NGSLD_E_CUDA, "TSV formatter launch failed");
+    c->stats.n_launches += rc;
+    CUDA_TRY(c, cudaEventRecord(b.ev_f1, c->s_main));
+    // total byte count first, then the text itself (size known only after the first copy)
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_text_len, b.d_line_off + n, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_main));
+  } else if (mode == MODE_ROWS) {
+    CUDA_TRY(c, cudaEventRecord(b.ev_f0, c->s_main));  // join point
+    CUDA_TRY(c, cudaStreamWaitEvent(c->s_copy, b.ev_f0, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, n * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
+    CUDA_TRY(c, cudaEventRecord(b.ev_done, c->s_copy));
+    c->stats.d2h_bytes += n * sizeof(ngsld_pair_row);
+  }
+  if (mode != MODE_ROWS) CUDA_TRY(c, cudaEventRecord(b.ev_done, c->s_main));
+  CUDA_TRY(c, cudaGetLastError());
+  b.n_rows = n;
+  b.pending = true;
+  return NGSLD_OK;
+}
+
+struct Delivery {
+  ScanMode mode;
+  int extend_out = 0;
+  ngsld_row_sink rows;
+  ngsld_text_sink text;
+  void *user;
+};
+
+int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
+  CUDA_TRY(c, cudaEventSynchronize(b.ev_done));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, b.ev_em0, b.ev_em1) == cudaSuccess) c->stats.ms_em += ms;
+  if (cudaEventElapsedTime(&ms, b.ev_p0, b.ev_p1) == cudaSuccess) c->stats.ms_pearson += ms;
+  b.pending = false;
+  c->stats.n_pairs += b.n_rows;
+  if (d.mode == MODE_TEXT) {
+    if (cudaEventElapsedTime(&ms, b.ev_f0, b.ev_f1) == cudaSuccess) c->stats.ms_format += ms;
+    unsigned long long bytes = b.h_text_len[0];
+    if (b.h_text_len[1] == 0) {
+      CUDA_TRY(c, cudaMemcpyAsync(b.h_text, b.d_text_out, bytes, cudaMemcpyDeviceToHost, c->s_copy));
+      CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+      c->stats.d2h_bytes += bytes + 16;
+    } else {
+      // some value was outside the device formatter's range: re-format this chunk with the host printf
+      CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, b.n_rows * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
+      CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+      c->stats.d2h_bytes += b.n_rows * sizeof(ngsld_pair_row);
+      std::string txt;
+      char line[2048];
+      for (uint64_t k = 0; k < b.n_rows; k++) {
+        const ngsld_pair_row &r = b.h_rows[k];
+        const char *l1 = c->have_labels ? c->h_labels[r.s1].c_str() : "(null)";
+        const char *l2 = c->have_labels ? c->h_labels[r.s2].c_str() : "(null)";
+        const int m = fmt::format_row_host(r, l1, l2, c->h_maf[r.s1], c->h_maf[r.s2], d.extend_out, line, sizeof line);
+        if (m < 0) return fail(c, NGSLD_E_INVALID, "row too long for the host formatter");
+        txt.append(line, m);
+      }
+      if (d.text && d.text(d.user, txt.data(), txt.size(), b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "text sink aborted the scan");
+      return NGSLD_OK;
+    }
+    if (d.text && d.text(d.user, b.h_text, bytes, b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "text sink aborted the scan");
+  } else if (d.mode == MODE_ROWS) {
+    if (d.rows && d.rows(d.user, b.h_rows, b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "row sink aborted the scan");
+  }
+  return NGSLD_OK;
+}
+
+int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *Pp, const Delivery &d) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!Pp) return fail(c, NGSLD_E_INVALID, "scan parameters missing");
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
+  const ngsld_scan_params P = *Pp;
+  if (!(P.rnd_sample > 0) || P.rnd_sample > 1) return fail(c, NGSLD_E_INVALID, "proportion of comparisons to sample must be in ]0,1]!");
+  if (P.min_maf < 0 || P.min_maf > 1) return fail(c, NGSLD_E_INVALID, "minimum allele frequency must be in [0,1]!");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  memset(&c->stats, 0, sizeof c->stats);
+  const double t_plan0 = now_ms();
+  Plan pl;
+  int rc = make_plan(c, s1_lo, s1_hi, P, pl);
+  if (rc) return rc;
+  rc = upload_plan(c, pl, P);
+  if (rc) return rc;
+  c->stats.ms_plan = now_ms() - t_plan0;
+  if (pl.total == 0) return NGSLD_OK;
+  EmChoice ch;
+  rc = choose_em(c, pl, ch);
+  if (rc) return rc;
+  fmt::FormatArgs fa;
+  memset(&fa, 0, sizeof fa);
+  uint32_t slot = 0;
+  if (d.mode == MODE_TEXT) {
+    fa.labels = c->have_labels ? c->d_label_blob : nullptr;
+    fa.label_off = c->d_label_off;
+    fa.maf = c->d_maf;
+    fa.extend_out = P.extend_out;
+    slot = fmt::slot_bytes(c->max_label_len, P.extend_out != 0);
+    fa.slot = slot;
+  }
+  uint64_t chunk = std::min<unsigned long long>(c->chunk_rows, pl.total);
+  if (d.mode == MODE_TEXT) chunk = std::min<uint64_t>(chunk, 1ull << 20);
+  const bool use_tiles = ch.tile && ch.v && !P.strict;
+  std::vector<uint2> tiles;
+  std::vector<size_t> block_off;
+  if (use_tiles) {
+    // whole A-blocks per chunk, so no tile is ever staged twice
+    build_tiles(pl, pl.c_lo, pl.c_hi, ch.TA, ch.TB, tiles, block_off);
+    for (size_t ab = 0; ab + 1 < block_off.size(); ab++) {
+      const uint32_t a = pl.c_lo + (uint32_t)ab * ch.TA, a_end = std::min<uint32_t>(pl.c_hi, a + ch.TA);
+      chunk = std::max<uint64_t>(chunk, pl.row_off[a_end] - pl.row_off[a]);
+    }
+    if (tiles.size() > c->cap_tiles) {
+      dfree(c->d_tiles);
+      c->cap_tiles = tiles.size() + 1024;
+      CUDA_TRY(c, cudaMalloc(&c->d_tiles, c->cap_tiles * sizeof(uint2)));
+    }
+    if (!tiles.empty()) {
+      CUDA_TRY(c, cudaMemcpy(c->d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+      c->stats.h2d_bytes += tiles.size() * sizeof(uint2);
+    }
+  }
+  rc = ensure_chunks(c, chunk, d.mode == MODE_ROWS, d.mode == MODE_TEXT, slot);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->s_main));
+  CUDA_TRY(c, cudaEventRecord(c->ev_begin, c->s_main));
+  unsigned long long r0 = 0;
+  size_t ab0 = 0;
+  int k = 0;
+  while (r0 < pl.total) {
+    ChunkBuf &b = c->buf[k & 1];
+    if (b.pending) {
+      rc = deliver_chunk(c, b, d);
+      if (rc) return rc;
+    }
+    unsigned long long r1;
+    size_t t0 = 0, t1 = 0;
+    if (use_tiles) {
+      size_t ab1 = ab0;
+      r1 = r0;
+      while (ab1 + 1 < block_off.size()) {
+        const uint32_t a_end = std::min<uint32_t>(pl.c_hi, pl.c_lo + (uint32_t)(ab1 + 1) * ch.TA);
+        if (pl.row_off[a_end] - r0 > chunk && ab1 > ab0) break;
+        r1 = pl.row_off[a_end];
+        ab1++;
+        if (r1 - r0 >= chunk) break;
+      }
+      t0 = block_off[ab0];
+      t1 = block_off[ab1];
+      ab0 = ab1;
+      if (r1 == r0) continue;  // A-blocks without pairs
+    } else {
+      r1 = std::min<unsigned long long>(pl.total, r0 + chunk);
+    }
+    rc = launch_chunk(c, pl, P, ch, b, r0, r1, t0, t1, d.mode, &fa);
+    if (rc) return rc;
+    r0 = r1;
+    k++;
+  }
+  for (int j = 0; j < 2; j++) {
+    ChunkBuf &b = c->buf[(k + j) & 1];
+    if (b.pending) {
+      rc = deliver_chunk(c, b, d);
+      if (rc) return rc;
+    }
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev_end, c->s_main));
+  CUDA_TRY(c, cudaEventSynchronize(c->ev_end));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.ms_device_total = ms;
+  DevCounters hc;
+  CUDA_TRY(c, cudaMemcpy(&hc, c->d_ctr, sizeof hc, cudaMemcpyDeviceToHost));
+  c->stats.sum_em_passes = hc.em_passes;
+  return NGSLD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int ngsld_abi_version(void) { return NGSLD_ABI_VERSION; }
+
+int ngsld_create(ngsld_ctx **out, int device) {
+  if (!out) return NGSLD_E_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); this library has no CPU fallback";
+    return NGSLD_E_CUDA;
+  }
+  if (device < 0 || device >= n_dev) {
+    g_create_error = "device index out of range";
+    return NGSLD_E_INVALID;
+  }
+  ngsld_ctx *c = new (std::nothrow) ngsld_ctx();
+  if (!c) return NGSLD_E_NOMEM;
+  c->device = device;
+  auto bail = [&](const char *what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    ngsld_destroy(c);
+    return NGSLD_E_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major != 10) {
+    g_create_error = "this build carries sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+    ngsld_destroy(c);
+    return NGSLD_E_CUDA;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&c->own_main, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  c->s_main = c->own_main;
+  for (auto &b : c->buf) {
+    cudaEvent_t *evs[] = {&b.ev_ready, &b.ev_em0, &b.ev_em1, &b.ev_p0, &b.ev_p1, &b.ev_f0, &b.ev_f1, &b.ev_done};
+    for (auto ev : evs)
+      if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("event", e);
+  }
+  if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaMalloc(&c->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+  *out = c;
+  return NGSLD_OK;
+}
+
+void ngsld_destroy(ngsld_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_chunks(c);
+  dfree(c->d_gl);
+  dfree(c->d_maf);
+  dfree(c->d_q);
+  dfree(c->d_dx_sig);
+  dfree(c->d_dx_se);
+  dfree(c->d_cum);
+  dfree(c->d_seg);
+  dfree(c->d_label_blob);
+  dfree(c->d_label_off);
+  dfree(c->d_cs);
+  dfree(c->d_cw_end);
+  dfree(c->d_row_off);
+  dfree(c->d_seeds);
+  dfree(c->d_counts);
+  dfree(c->d_tiles);
+  dfree(c->d_ctr);
+  for (auto &b : c->buf) {
+    cudaEvent_t evs[] = {b.ev_ready, b.ev_em0, b.ev_em1, b.ev_p0, b.ev_p1, b.ev_f0, b.ev_f1, b.ev_done};
+    for (auto ev : evs)
+      if (ev) cudaEventDestroy(ev);
+  }
+  if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+  if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->own_main) cudaStreamDestroy(c->own_main);
+  if (c->s_aux) cudaStreamDestroy(c->s_aux);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  delete c;
+}
+
+const char *ngsld_last_error(const ngsld_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ngsld_set_stream(ngsld_ctx *c, void *stream) {
+  if (!c) return NGSLD_E_INVALID;
+  c->s_main = stream ? (cudaStream_t)stream : c->own_main;
+  return NGSLD_OK;
+}
+
+int ngsld_set_chunk_rows(ngsld_ctx *c, uint64_t rows) {
+  if (!c) return NGSLD_E_INVALID;
+  c->chunk_rows = rows ? rows : (4ull << 20);
+  return NGSLD_OK;
+}
+
+int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int log_scale, int from_log_cells,
+                        int ignore_miss_data, int call_geno, double N_thresh, double call_thresh, int n_threads,
+                        double *gl, double *expg, double *maf) {
+  if (!raw || !gl || !expg || !maf || n_sites == 0 || n_ind == 0) return NGSLD_E_INVALID;
+  if (call_geno && N_thresh > call_thresh) return NGSLD_E_INVALID;  // gen_func.cpp:887-888
+  hostprep::PrepOptions o;
+  o.log_scale = log_scale != 0;
+  o.from_log_cells = from_log_cells != 0;
+  o.ignore_miss = ignore_miss_data != 0;
+  o.call_geno = call_geno != 0;
+  o.n_thresh = N_thresh;
+  o.call_thresh = call_thresh;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  return hostprep::prepare_sites(raw, n_sites, n_ind, o, n_threads, gl, expg, maf) == 0 ? NGSLD_OK : NGSLD_E_DATA;
+}
+
+int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
+                    uint64_t n_ind) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!gl || !expg || !maf || n_sites == 0 || n_ind == 0) return fail(c, NGSLD_E_INVALID, "null or empty site arrays");
+  if (n_sites >= (1ull << 32) - 1) return fail(c, NGSLD_E_INVALID, "n_sites must be below 2^32-1");
+  for (uint64_t s = 0; s < n_sites; s++)
+    if (maf[s] < 0 || maf[s] > 1) return fail(c, NGSLD_E_DATA, "invalid allele frequencies");  // gen_func.cpp:1030
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  dfree(c->d_gl);
+  dfree(c->d_maf);
+  dfree(c->d_q);
+  dfree(c->d_dx_sig);
+  dfree(c->d_dx_se);
+  dfree(c->d_cum);
+  dfree(c->d_seg);
+  dfree(c->d_label_blob);
+  dfree(c->d_label_off);
+  c->have_pos = c->have_labels = false;
+  c->n_sites = n_sites;
+  c->n_ind = n_ind;
+  c->n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
+  const size_t row_bytes = c->n_pad * 24;
+  CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
+  CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * c->n_pad * sizeof(uint64_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * c->n_pad * sizeof(uint16_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_seg, 0, n_sites * sizeof(uint32_t), c->s_main));
+  if (c->n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * row_bytes, c->s_main));
+  CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, row_bytes, gl, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_maf, maf, n_sites * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+  c->h_maf.assign(maf, maf + n_sites);
+  // per-site x87 terms of the expected-genotype correlation, on the host FPU
+  std::vector<uint64_t> sig(n_sites * c->n_pad);
+  std::vector<uint16_t> se(n_sites * c->n_pad);
+  std::vector<double> q(n_sites);
+  const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
+  hostprep::pearson_site_terms(expg, n_sites, n_ind, c->n_pad, nt, sig.data(), se.data(), q.data());
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  c->h_seg.assign(n_sites, 0);
+  c->h_cum.assign(n_sites, 0.0);
+  return NGSLD_OK;
+}
+
+int ngsld_set_positions(ngsld_ctx *c, const double *pos_dist, const char *const *labels) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must come first");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const uint64_t n = c->n_sites;
+  c->have_pos = false;
+  if (pos_dist) {
+    // exact prefix sums: every finite gap must be a non-negative integer and the total below 2^53, so that
+    // cum[s2]-cum[s1] equals the reference's running double sum (ngsLD.cpp:241) bit for bit
+    double acc = 0;
+    uint32_t seg = 0;
+    for (uint64_t s = 0; s < n; s++) {
+      const double g = pos_dist[s];
+      if (isinf(g) && g > 0) {
+        if (s > 0) seg++;
+      } else {
+        if (!(g >= 0) || g != floor(g)) return fail(c, NGSLD_E_DATA, "inter-site distances must be non-negative integers or +inf");
+        if (s > 0) acc += g;  // pos_dist[0] (distance from the origin) never enters a pair distance
+        if (acc > 9007199254740992.0) return fail(c, NGSLD_E_DATA, "positions exceed 2^53");
+      }
+      c->h_cum[s] = acc;
+      c->h_seg[s] = seg;
+    }
+    dfree(c->d_cum);
+    CUDA_TRY(c, cudaMalloc(&c->d_cum, n * sizeof(double)));
+    CUDA_TRY(c, cudaMemcpy(c->d_cum, c->h_cum.data(), n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_seg, c->h_seg.data(), n * 4, cudaMemcpyHostToDevice));
+    c->have_pos = true;
+  }
+  dfree(c->d_label_blob);
+  dfree(c->d_label_off);
+  c->have_labels = false;
+  c->max_label_len = 6;
+  if (labels) {
+    std::vector<uint32_t> off(n + 1);
+    std::string blob;
+    c->h_labels.assign(n, std::string());
+    uint32_t mx = 0;
+    for (uint64_t s = 0; s < n; s++) {
+      off[s] = (uint32_t)blob.size();
+      const char *l = labels[s] ? labels[s] : "(null)";
+      const size_t len = strlen(l);
+      if (blob.size() + len >= (1ull << 32)) return fail(c, NGSLD_E_INVALID, "labels exceed 4 GiB");
+      blob.append(l, len);
+      c->h_labels[s].assign(l, len);
+      mx = std::max<uint32_t>(mx, (uint32_t)len);
+    }
+    off[n] = (uint32_t)blob.size();
+    CUDA_TRY(c, cudaMalloc(&c->d_label_blob, std::max<size_t>(blob.size(), 1)));
+    CUDA_TRY(c, cudaMalloc(&c->d_label_off, (n + 1) * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMemcpy(c->d_label_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_label_off, off.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    c->have_labels = true;
+    c->max_label_len = std::max<uint32_t>(mx, 1);
+  }
+  return NGSLD_OK;
+}
+
+void ngsld_scan_defaults(ngsld_scan_params *p) {  // reference parse_args.cpp:6-29
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  p->max_kb_dist = 100;
+  p->max_snp_dist = 0;
+  p->min_maf = 0;
+  p->rnd_sample = 1;
+  p->seed = 1;
+}
+
+int ngsld_scan_count(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, uint64_t *n_rows) {
+  if (!c || !p || !n_rows) return NGSLD_E_INVALID;
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Plan pl;
+  int rc = make_plan(c, s1_lo, s1_hi, *p, pl);
+  if (rc) return rc;
+  if (pl.sampled) {
+    rc = upload_plan(c, pl, *p);
+    if (rc) return rc;
+  }
+  *n_rows = pl.total;
+  return NGSLD_OK;
+}
+
+int ngsld_partition(ngsld_ctx *c, const ngsld_scan_params *p, int n_parts, uint64_t *bounds) {
+  if (!c || !p || !bounds || n_parts < 1) return NGSLD_E_INVALID;
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Plan pl;
+  int rc = make_plan(c, 0, c->n_sites, *p, pl);
+  if (rc) return rc;
+  if (pl.sampled) {
+    rc = upload_plan(c, pl, *p);
+    if (rc) return rc;
+  }
+  bounds[0] = 0;
+  for (int k = 1; k < n_parts; k++) {
+    const unsigned long long target = (unsigned long long)((long double)pl.total * k / n_parts);
+    // first compact site whose rows start at or after the target
+    auto it = std::lower_bound(pl.row_off.begin(), pl.row_off.begin() + pl.n_compact, target);
+    const size_t cidx = it - pl.row_off.begin();
+    uint64_t s = cidx < pl.n_compact ? pl.cs[cidx] : c->n_sites;
+    if (s < bounds[k - 1]) s = bounds[k - 1];
+    bounds[k] = s;
+  }
+  bounds[n_parts] = c->n_sites;
+  return NGSLD_OK;
+}
+
+int ngsld_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_row_sink sink, void *user) {
+  Delivery d;
+  d.mode = MODE_ROWS;
+  d.rows = sink;
+  d.text = nullptr;
+  d.user = user;
+  return run_scan(c, s1_lo, s1_hi, p, d);
+}
+
+namespace {
+struct IntoState {
+  ngsld_pair_row *out;
+  uint64_t cap, n;
+};
+int into_sink(void *u, const ngsld_pair_row *rows, uint64_t n) {
+  IntoState *st = (IntoState *)u;
+  if (st->n + n > st->cap) return 1;
+  memcpy(st->out + st->n, rows, n * sizeof(ngsld_pair_row));
+  st->n += n;
+  return 0;
+}
+}  // namespace
+
+int ngsld_scan_into(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_pair_row *out,
+                    uint64_t cap, uint64_t *n_rows) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!out && cap) return fail(c, NGSLD_E_INVALID, "output buffer missing");
+  IntoState st = {out, cap, 0};
+  Delivery d;
+  d.mode = MODE_ROWS;
+  d.rows = into_sink;
+  d.text = nullptr;
+  d.user = &st;
+  int rc = run_scan(c, s1_lo, s1_hi, p, d);
+  if (rc == NGSLD_E_SINK) return fail(c, NGSLD_E_INVALID, "output buffer too small for this scan");
+  if (n_rows) *n_rows = st.n;
+  return rc;
+}
+
+int ngsld_scan_tsv(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_text_sink sink,
+                   void *user) {
+  Delivery d;
+  d.mode = MODE_TEXT;
+  d.extend_out = p ? p->extend_out : 0;
+  d.rows = nullptr;
+  d.text = sink;
+  d.user = user;
+  return run_scan(c, s1_lo, s1_hi, p, d);
+}
+
+int ngsld_scan_device(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p) {
+  Delivery d;
+  d.mode = MODE_DEVICE;
+  d.rows = nullptr;
+  d.text = nullptr;
+  d.user = nullptr;
+  return run_scan(c, s1_lo, s1_hi, p, d);
+}
+
+int ngsld_get_stats(const ngsld_ctx *c, ngsld_scan_stats *out) {
+  if (!c || !out) return NGSLD_E_INVALID;
+  *out = c->stats;
+  return NGSLD_OK;
+}
+
+int ngsld_pairs(ngsld_ctx *c, const uint32_t *s1, const uint32_t *s2, uint64_t n_pairs, int ignore_miss_data,
+                int strict, ngsld_pair_row *out) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called first");
+  if (n_pairs == 0) return NGSLD_OK;
+  if (!s1 || !s2 || !out) return fail(c, NGSLD_E_INVALID, "null pair arrays");
+  for (uint64_t k = 0; k < n_pairs; k++)
+    if (s1[k] >= c->n_sites || s2[k] >= c->n_sites) return fail(c, NGSLD_E_INVALID, "site index out of range");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  memset(&c->stats, 0, sizeof c->stats);
+  Plan pl;  // only used for kernel choice (list path)
+  pl.sampled = true;
+  EmChoice ch;
+  int rc = choose_em(c, pl, ch);
+  if (rc) return rc;
+  const uint64_t chunk = std::min<uint64_t>(c->chunk_rows, n_pairs);
+  rc = ensure_chunks(c, chunk, true, false, 0);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->s_main));
+  const SiteTable T = site_table(c);
+  ngsld_scan_params P;
+  ngsld_scan_defaults(&P);
+  P.ignore_miss_data = ignore_miss_data;
+  P.strict = strict;
+  for (uint64_t r0 = 0; r0 < n_pairs; r0 += chunk) {
+    const uint64_t n = std::min<uint64_t>(chunk, n_pairs - r0);
+    ChunkBuf &b = c->buf[0];
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_s1, s1 + r0, n * 4, cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(c, cudaMemcpyAsync(b.d_s2, s2 + r0, n * 4, cudaMemcpyHostToDevice, c->s_main));
+    PairChunk C;
+    C.s1 = b.d_s1;
+    C.s2 = b.d_s2;
+    C.rows = b.d_rows;
+    C.n_pairs = n;
+    const unsigned gb = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 32);
+    aux::fill_rows_kernel<<<gb, 256, 0, c->s_main>>>(T, C);
+    const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
+    aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C);
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
+    if (strict || !ch.v) {
+      aux::em_strict_kernel<<<pb, 128, 0, c->s_main>>>(T, C, ignore_miss_data, c->d_ctr);
+    } else {
+      int ign = ignore_miss_data;
+      SiteTable Tt = T;
+      PairChunk Cc = C;
+      DevCounters *ctr = c->d_ctr;
+      void *args[] = {&Tt, &Cc, &ign, &ctr};
+      const unsigned long long gpc = emfast::CTA_THREADS / ch.v->lpg;
+      const unsigned blocks = (unsigned)std::min<unsigned long long>((n + gpc - 1) / gpc, ch.blocks_list);
+      CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, 0, c->s_main));
+    }
+    c->stats.n_launches += 3;
+    CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, n * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_main));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+    CUDA_TRY(c, cudaGetLastError());
+    memcpy(out + r0, b.h_rows, n * sizeof(ngsld_pair_row));
+    c->stats.n_pairs += n;
+  }
+  return NGSLD_OK;
+}
+
+int ngsld_site_seeds(uint64_t seed, uint64_t n_sites, uint64_t *out) {
+  if (!out && n_sites) return NGSLD_E_INVALID;
+  hostprep::site_seeds(seed, n_sites, out);
+  return NGSLD_OK;
+}
+
+int ngsld_tsv_header(int extend_out, char *buf, size_t cap) {  // reference ngsLD.cpp:77
+  const char *base = "site1\tsite2\tdist\tr2_ExpG\tD\tDp\tr2";
+  const char *ext = "\tsample_size\tmaf1\tmaf2\thap00\thap01\thap10\thap11\thap_maf1\thap_maf2\tchi2\tloglike\tnIter";
+  int n = snprintf(buf, cap, "%s%s\n", base, extend_out ? ext : "");
+  return (n < 0 || (size_t)n >= cap) ? NGSLD_E_INVALID : n;
+}
+
+int ngsld_probe_fp64(ngsld_ctx *c, double *gflops) {
+  if (!c || !gflops) return NGSLD_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int blocks = c->sm_count * 8, threads = 256, iters = 20000;
+  double *d = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  aux::fp64_probe_kernel<<<blocks, threads, 0, c->s_main>>>(d, 1000);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, c->s_main);
+    aux::fp64_probe_kernel<<<blocks, threads, 0, c->s_main>>>(d, iters);
+    cudaEventRecord(e1, c->s_main);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  CUDA_TRY(c, cudaGetLastError());
+  *gflops = (double)blocks * threads * iters * 8.0 * 2.0 / (best * 1e-3) / 1e9;
+  return NGSLD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// x87 extended-precision (64-bit significand) arithmetic in integer registers.
+//
+// The reference's r2_ExpG column is gsl_stats_correlation (reference ngsLD.cpp:365-367), whose
+// accumulators are `long double`; on x86-64 that is the x87 80-bit format, round-to-nearest-even,
+// 64-bit precision control.  To reproduce that column bit for bit on a GPU (no fp80 hardware) the
+// per-pair part of the recurrence -- two multiplies and one add per individual, one divide per
+// pair -- is carried out here on (sign, exponent, 64-bit significand) triples.
+//
+// Only zero and normal numbers are representable (no x87 denormals / inf / nan): the operands are
+// differences and products of expected genotypes in [0,2], > 16000 binades away from either end
+// of the x87 exponent range.  Compiles as plain C++ too (tests/test_fp80.py checks it against the
+// host FPU's native long double).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define X87_HD __host__ __device__ __forceinline__
+#else
+#define X87_HD static inline
+#endif
+
+namespace x87 {
+
+struct ext {       // value = (-1)^neg * sig * 2^(exp - 63);  sig == 0 -> zero, else bit 63 set
+  uint64_t sig;
+  int32_t exp;
+  uint32_t neg;
+};
+
+X87_HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll(v);
+#endif
+}
+
+X87_HD void mul64(uint64_t a, uint64_t b, uint64_t &hi, uint64_t &lo) {
+#if defined(__CUDA_ARCH__)
+  hi = __umul64hi(a, b);
+  lo = a * b;
+#else
+  unsigned __int128 p = (unsigned __int128)a * b;
+  hi = (uint64_t)(p >> 64);
+  lo = (uint64_t)p;
+#endif
+}
+
+// Round a 128-bit significand (hi:lo, hi normalised) plus a sticky flag to 64 bits, ties to even.
+X87_HD ext round_pack(uint32_t neg, int32_t exp, uint64_t hi, uint64_t lo, bool sticky) {
+  bool guard = (lo >> 63) != 0;
+  bool rest = ((lo << 1) != 0) || sticky;
+  if (guard && (rest || (hi & 1))) {
+    hi += 1;
+    if (hi == 0) {  // carried out of 64 bits
+      hi = 0x8000000000000000ull;
+      exp += 1;
+    }
+  }
+  ext r;
+  r.sig = hi;
+  r.exp = exp;
+  r.neg = neg;
+  return r;
+}
+
+X87_HD ext zero(uint32_t neg = 0) {
+  ext r;
+  r.sig = 0;
+  r.exp = 0;
+  r.neg = neg;
+  return r;
+}
+
+// Exact widening of an IEEE double (finite; subnormals handled) -- the x87 FLD m64.
+X87_HD ext from_double(double d) {
+#if defined(__CUDA_ARCH__)
+  uint64_t b = (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t b;
+  __builtin_memcpy(&b, &d, 8);
+#endif
+  uint32_t neg = (uint32_t)(b >> 63);
+  int32_t be = (int32_t)((b >> 52) & 0x7ff);
+  uint64_t frac = b & 0xfffffffffffffull;
+  if (be == 0) {
+    if (frac == 0) return zero(neg);
+    int sh = clz64(frac);
+    ext r;
+    r.sig = frac << sh;
+    r.exp = -1022 - 52 + (63 - sh);
+    r.neg = neg;
+    return r;
+  }
+  ext r;
+  r.sig = (frac | 0x10000000000000ull) << 11;
+  r.exp = be - 1023;
+  r.neg = neg;
+  return r;
+}
+
+// The 10-byte memory image of a long double: sig = bytes 0-7, se = bytes 8-9 (sign | biased exp).
+X87_HD ext from_bits(uint64_t sig, uint16_t se) {
+  ext r;
+  r.sig = sig;
+  r.exp = (int32_t)(se & 0x7fff) - 16383;
+  r.neg = (uint32_t)(se >> 15);
+  if (sig == 0) r.exp = 0;
+  return r;
+}
+
+X87_HD ext mul(const ext &a, const ext &b) {
+  uint32_t neg = a.neg ^ b.neg;
+  if (a.sig == 0 || b.sig == 0) return zero(neg);
+  uint64_t hi, lo;
+  mul64(a.sig, b.sig, hi, lo);
+  int32_t e = a.exp + b.exp + 1;
+  if (!(hi >> 63)) {  // product in [2^126, 2^127): renormalise
+    hi = (hi << 1) | (lo >> 63);
+    lo <<= 1;
+    e -= 1;
+  }
+  return round_pack(neg, e, hi, lo, false);
+}
+
+X87_HD ext add(const ext &x, const ext &y) {
+  if (y.sig == 0) {
+    if (x.sig == 0) return zero(x.neg & y.neg);  // (+0)+(-0) = +0 under round-to-nearest
+    return x;
+  }
+  if (x.sig == 0) return y;
+  // a = operand of larger magnitude
+  bool swap = (y.exp > x.exp) || (y.exp == x.exp && y.sig > x.sig);
+  const ext &a = swap ? y : x;
+  const ext &b = swap ? x : y;
+  uint32_t d = (uint32_t)(a.exp - b.exp);
+  // b's significand as a 128-bit value aligned under a (a = a.sig:0), jamming lost bits into `sticky`
+  uint64_t bhi, blo;
+  bool sticky = false;
+  if (d == 0) {
+    bhi = b.sig;
+    blo = 0;
+  } else if (d < 64) {
+    bhi = b.sig >> d;
+    blo = b.sig << (64 - d);
+  } else if (d == 64) {
+    bhi = 0;
+    blo = b.sig;
+  } else if (d < 128) {
+    bhi = 0;
+    blo = b.sig >> (d - 64);
+    sticky = (b.sig << (128 - d)) != 0;
+  } else {
+    bhi = 0;
+    blo = 0;
+    sticky = true;
+  }
+  uint64_t hi, lo;
+  int32_t e = a.exp;
+  if (a.neg == b.neg) {
+    lo = blo;
+    hi = a.sig + bhi;
+    if (hi < a.sig) {  // carry out of bit 127: shift right one
+      sticky = sticky || (lo & 1);
+      lo = (lo >> 1) | (hi << 63);
+      hi = (hi >> 1) | 0x8000000000000000ull;
+      e += 1;
+    }
+    return round_pack(a.neg, e, hi, lo, sticky);
+  }
+  // magnitude subtraction a - b - (sticky ? tiny : 0)
+  uint64_t borrow_in = sticky ? 1 : 0;  // lost bits of b make the true difference slightly smaller
+  uint64_t lo0 = 0 - blo;
+  uint64_t br = (blo != 0) ? 1 : 0;
+  lo = lo0 - borrow_in;
+  if (lo0 < borrow_in) br = 1;
+  hi = a.sig - bhi - br;
+  // (with sticky set, lo now holds the floor of the difference and the remainder is still non-zero)
+  if (hi == 0 && lo == 0) return zero(0);
+  if (hi == 0) {
+    hi = lo;
+    lo = 0;
+    e -= 64;
+  }
+  int sh = clz64(hi);
+  if (sh) {
+    hi = (hi << sh) | (lo >> (64 - sh));
+    lo <<= sh;
+    e -= sh;
+  }
+  return round_pack(a.neg, e, hi, lo, sticky);
+}
+
+// Correctly rounded quotient; b != 0.
+X87_HD ext div(const ext &a, const ext &b) {
+  uint32_t neg = a.neg ^ b.neg;
+  if (a.sig == 0) return zero(neg);
+  // Scale the numerator so the quotient of significands lies in [1, 2); then restoring division.
+  uint64_t rem;
+  int32_t e = a.exp - b.exp;
+  if (a.sig >= b.sig) {
+    rem = a.sig - b.sig;
+  } else {
+    rem = a.sig - (b.sig - a.sig);  // 2*a.sig - b.sig, which fits because a.sig < b.sig
+    e -= 1;
+  }
+  uint64_t q = 1;
+  for (int k = 0; k < 63; k++) {
+    bool top = (rem >> 63) != 0;
+    rem <<= 1;
+    bool bit = top || rem >= b.sig;
+    if (bit) rem -= b.sig;
+    q = (q << 1) | (bit ? 1 : 0);
+  }
+  bool top = (rem >> 63) != 0;
+  rem <<= 1;
+  bool guard = top || rem >= b.sig;
+  if (guard) rem -= b.sig;
+  return round_pack(neg, e, q, guard ? 0x8000000000000000ull : 0, rem != 0);
+}
+
+// Narrow to double with round-to-nearest-even (x87 FSTP m64); overflow -> inf, underflow -> subnormal/0.
+X87_HD double to_double(const ext &a) {
+  uint64_t bits;
+  uint64_t sign = (uint64_t)a.neg << 63;
+  if (a.sig == 0) {
+    bits = sign;
+  } else {
+    int32_t e = a.exp;
+    uint64_t m = a.sig;
+    int drop = 11;
+    if (e < -1022) drop += (-1022 - e);
+    if (drop > 64) {
+      bits = sign;  // far below the smallest subnormal
+    } else {
+      uint64_t kept, lost;
+      bool half, rest;
+      if (drop == 64) {
+        kept = 0;
+        lost = m;
+      } else {
+        kept = m >> drop;
+        lost = m << (64 - drop);
+      }
+      half = (lost >> 63) != 0;
+      rest = (lost << 1) != 0;
+      if (half && (rest || (kept & 1))) kept += 1;
+      if (e < -1022) {
+        bits = sign | kept;  // subnormal (a carry into bit 52 lands on the smallest normal correctly)
+      } else {
+        if (kept >> 53) {
+          kept >>= 1;
+          e += 1;
+        }
+        if (e > 1023)
+          bits = sign | 0x7ff0000000000000ull;
+        else
+          bits = sign | ((uint64_t)(e + 1023) << 52) | (kept & 0xfffffffffffffull);
+      }
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)bits);
+#else
+  double d;
+  __builtin_memcpy(&d, &bits, 8);
+  return d;
+#endif
+}
+
+}  // namespace x87

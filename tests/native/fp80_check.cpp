@@ -1,0 +1,65 @@
+// Host self-check of ngsld_b200/csrc/fp80.cuh against the FPU's native long double (x87).
+// Built and run by tests/test_fp80.py.  Exit code 0 = all identical.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include "../../ngsld_b200/csrc/fp80.cuh"
+
+static x87::ext from_ld(long double v) {
+  uint64_t sig;
+  uint16_t se;
+  memcpy(&sig, &v, 8);
+  memcpy(&se, (char *)&v + 8, 2);
+  return x87::from_bits(sig, se);
+}
+static bool same(const x87::ext &a, long double v) {
+  x87::ext b = from_ld(v);
+  if (a.sig == 0 && b.sig == 0) return a.neg == b.neg;
+  return a.sig == b.sig && a.exp == b.exp && a.neg == b.neg;
+}
+
+int main(int argc, char **argv) {
+  long n = argc > 1 ? atol(argv[1]) : 2000000;
+  std::mt19937_64 g(12345);
+  std::uniform_real_distribution<double> U(-2.0, 2.0);
+  long bad = 0;
+  auto rnd_ld = [&](int spread) {
+    // random long double with full 64-bit significand and modest exponent spread
+    long double v = (long double)U(g) + (long double)U(g) * 0x1p-40L + (long double)U(g) * 0x1p-62L;
+    int sh = (int)(g() % (2 * spread + 1)) - spread;
+    return ldexpl(v, sh);
+  };
+  for (long k = 0; k < n; k++) {
+    int spread = (k % 5 == 0) ? 140 : (k % 5 == 1 ? 70 : 3);
+    volatile long double a = rnd_ld(spread), b = rnd_ld(spread);
+    if (k % 97 == 0) b = -a;                      // exact cancellation
+    if (k % 101 == 0) b = -a * (1 + 0x1p-63L);    // massive cancellation
+    if (k % 103 == 0) a = 0.0L;
+    if (k % 107 == 0) b = ldexpl(b, -64);         // alignment distance exactly at the guard boundary
+    if (k % 109 == 0) b = ldexpl(b, -65);
+    volatile long double s = a + b, p = a * b;
+    x87::ext ea = from_ld(a), eb = from_ld(b);
+    if (!same(x87::add(ea, eb), s)) { if (bad++ < 5) printf("add mismatch %La %La\n", (long double)a, (long double)b); }
+    if (!same(x87::mul(ea, eb), p)) { if (bad++ < 5) printf("mul mismatch %La %La\n", (long double)a, (long double)b); }
+    if (b != 0.0L) {
+      volatile long double q = a / b;
+      if (!same(x87::div(ea, eb), q)) { if (bad++ < 5) printf("div mismatch %La %La\n", (long double)a, (long double)b); }
+    }
+    volatile double d = (double)a;
+    double mine = x87::to_double(ea);
+    if (memcmp(&mine, (const void *)&d, 8) != 0) { if (bad++ < 5) printf("to_double mismatch %La\n", (long double)a); }
+    double dd = U(g) * std::ldexp(1.0, (int)(g() % 60) - 30);
+    if (!same(x87::from_double(dd), (long double)dd)) { if (bad++ < 5) printf("from_double mismatch %a\n", dd); }
+  }
+  // narrowing into the subnormal / overflow ranges of double
+  for (int e = -1090; e <= -1010; e++) {
+    volatile long double a = ldexpl(1.0L + 0x1.123456789abcdp-1L + 0x1p-60L, e);
+    volatile double d = (double)a;
+    double mine = x87::to_double(from_ld(a));
+    if (memcmp(&mine, (const void *)&d, 8) != 0) { if (bad++ < 5) printf("subnormal narrowing mismatch e=%d\n", e); }
+  }
+  printf("checked %ld random operand pairs, %ld mismatches\n", n, bad);
+  return bad ? 1 : 0;
+}

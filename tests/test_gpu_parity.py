@@ -1,0 +1,176 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle and the
+golden reference outputs.  Bars: strict kernel bit-exact in every column and byte-identical TSV; fast
+kernel r2_ExpG bit-exact, D/D'/r2 within 1e-9 at equal nIter (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import ngsld_b200 as N
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [(fx, v) for fx in ("edge", "tiny") for v in H.MANIFEST["fixtures"][fx]["variants"]]
+MID = [("s", "ext"), ("s", "rnd01"), ("s", "kb20")]
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_helpers
+    return gpu_helpers
+
+
+def _run_tsv(G, fx, variant, tmp, strict):
+    v = H.MANIFEST["fixtures"][fx]["variants"][variant]
+    raw, labels, dist, opt = H.load_fixture(fx, tmp, v["flags"], v["pos"], v.get("geno"))
+    eng, _ = G.engine_for(raw, opt, labels, dist)
+    with eng:
+        return eng.scan_tsv(G.scan_params(opt, strict)), v
+
+
+@pytest.mark.parametrize("fx,variant", SMALL + MID)
+def test_strict_tsv_is_byte_identical_to_reference(G, fx, variant, tmp_path_factory):
+    got, v = _run_tsv(G, fx, variant, tmp_path_factory.getbasetemp(), strict=True)
+    gold = H.golden_bytes(fx, variant)
+    if gold is not None:
+        assert got == gold
+    assert H.md5(got) == v["md5"]
+
+
+def _parse(tsv):
+    lines = tsv.decode().splitlines()
+    head = lines[0].split("\t")
+    rows = [l.split("\t") for l in lines[1:]]
+    return head, rows
+
+
+@pytest.mark.parametrize("fx,variant", SMALL + MID)
+def test_fast_tsv_matches_reference_within_contract(G, fx, variant, tmp_path_factory):
+    tmp = tmp_path_factory.getbasetemp()
+    got, v = _run_tsv(G, fx, variant, tmp, strict=False)
+    gold = H.golden_bytes(fx, variant)
+    if gold is None:
+        gold = H.oracle_tsv(fx, tmp, v["flags"], v["pos"], v.get("geno"))
+        assert H.md5(gold) == v["md5"]
+    hg, rg = _parse(got)
+    hr, rr = _parse(gold)
+    assert hg == hr and len(rg) == len(rr)
+    col = {n: i for i, n in enumerate(hr)}
+    exact = ["site1", "site2", "dist", "r2_ExpG"] + [c for c in ("sample_size", "maf1", "maf2", "loglike", "nIter") if c in col]
+    for a, b in zip(rg, rr):
+        for c in exact:
+            assert a[col[c]] == b[col[c]], (c, a, b)
+        for c in hr:
+            if c in exact:
+                continue
+            x, y = a[col[c]], b[col[c]]
+            if x != y:  # text may differ in the last printed digit only
+                assert abs(float(x) - float(y)) <= 1.000001e-6 * max(1.0, abs(float(y))), (c, x, y)
+
+
+@pytest.mark.parametrize("fx,variant", [("tiny", "ext"), ("tiny", "nomiss"), ("edge", "ext"), ("s", "ext")])
+def test_rows_strict_bit_exact_and_fast_within_tolerance(G, fx, variant, tmp_path_factory):
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"][fx]["variants"][variant]
+    raw, labels, dist, opt = H.load_fixture(fx, tmp, v["flags"], v["pos"], v.get("geno"))
+    eng, arrays = G.engine_for(raw, opt, labels, dist)
+    with eng:
+        strict = eng.scan(G.scan_params(opt, True))
+        fast = eng.scan(G.scan_params(opt, False))
+    assert len(strict) == v["rows"] == len(fast)
+    sel = np.arange(len(strict)) if len(strict) <= 3000 else np.random.default_rng(0).choice(len(strict), 3000, False)
+    ref = G.oracle_rows(arrays, strict["s1"][sel], strict["s2"][sel], opt["ignore_miss"])
+    G.assert_strict_equal(strict[sel], ref)
+    G.assert_fast_close(fast[sel], ref)
+    # fast vs strict over ALL rows (both on the GPU)
+    G.assert_fast_close(fast, strict)
+    assert np.array_equal(fast["s1"], strict["s1"]) and np.array_equal(fast["s2"], strict["s2"])
+    assert np.array_equal(fast["dist"], strict["dist"])
+
+
+# every (individuals-per-lane, lanes-per-group) kernel instantiation family, incl. ragged tails
+@pytest.mark.parametrize("n_ind", [1, 2, 3, 7, 24, 32, 33, 64, 65, 100, 128, 129, 250, 256, 257, 500, 513, 1000, 1025, 2047])
+@pytest.mark.parametrize("ignore_miss", [False, True])
+def test_every_group_shape_against_oracle(G, n_ind, ignore_miss):
+    n_sites = 14 if n_ind <= 256 else 8
+    GL, _ = H.gen_synth.synth(n_sites, n_ind, 1000 + n_ind)
+    opt = H.parse_flags(["--max_kb_dist", "0"] + (["--ignore_miss_data"] if ignore_miss else []))
+    eng, arrays = G.engine_for(GL, opt)
+    s1, s2 = np.triu_indices(n_sites, 1)
+    ref = G.oracle_rows(arrays, s1, s2, ignore_miss)
+    with eng:
+        G.assert_strict_equal(eng.pairs(s1, s2, ignore_miss, strict=True), ref)
+        G.assert_fast_close(eng.pairs(s1, s2, ignore_miss, strict=False), ref)
+        p = G.scan_params(opt, False)
+        rows = eng.scan(p)            # window path (tile kernel where it applies)
+        assert np.array_equal(rows["s1"], s1) and np.array_equal(rows["s2"], s2)
+        G.assert_fast_close(rows, ref)
+
+
+@pytest.mark.parametrize("path", ["list", "tile"])
+def test_list_and_tile_paths_agree_bitwise(G, path, tmp_path_factory, monkeypatch):
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"]["s"]["variants"]["kb20"]
+    raw, labels, dist, opt = H.load_fixture("s", tmp, v["flags"], True)
+    eng, _ = G.engine_for(raw, opt, labels, dist)
+    with eng:
+        monkeypatch.setenv("NGSLD_EM_PATH", path)
+        a = eng.scan(G.scan_params(opt, False))
+        monkeypatch.setenv("NGSLD_EM_PATH", "list")
+        b = eng.scan(G.scan_params(opt, False))
+    assert a.tobytes() == b.tobytes()
+
+
+def test_small_chunks_and_ranges_concatenate_to_the_whole(G, tmp_path_factory):
+    """Chunked streaming and first-site range partitioning (the multi-GPU sharding unit) must not change a byte."""
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"]["s"]["variants"]["ext"]
+    raw, labels, dist, opt = H.load_fixture("s", tmp, v["flags"], True)
+    eng, _ = G.engine_for(raw, opt, labels, dist)
+    p = G.scan_params(opt, False)
+    with eng:
+        whole = eng.scan_tsv(p, header=False)
+        eng.set_chunk_rows(777)
+        assert eng.scan_tsv(p, header=False) == whole
+        eng.set_chunk_rows(0)
+        bounds = eng.partition(p, 3)
+        assert bounds[0] == 0 and bounds[-1] == eng.n_sites and np.all(np.diff(bounds.astype(np.int64)) >= 0)
+        parts = [eng.scan_tsv(p, int(bounds[k]), int(bounds[k + 1]), header=False) for k in range(3)]
+        counts = [eng.count(p, int(bounds[k]), int(bounds[k + 1])) for k in range(3)]
+    assert b"".join(parts) == whole
+    assert sum(counts) == v["rows"] and max(counts) - min(counts) < 2 * eng.n_sites
+
+
+def test_sampling_reproduces_reference_pair_set(G, tmp_path_factory):
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"]["s"]["variants"]["rnd01"]
+    raw, labels, dist, opt = H.load_fixture("s", tmp, v["flags"], True)
+    eng, arrays = G.engine_for(raw, opt, labels, dist)
+    with eng:
+        rows = eng.scan(G.scan_params(opt, False))
+    assert len(rows) == v["rows"] == 789
+    gold = H.oracle_tsv("s", tmp, v["flags"], True).decode().splitlines()[1:]
+    want = [tuple(l.split("\t")[:2]) for l in gold]
+    got = [(labels[a], labels[b]) for a, b in zip(rows["s1"], rows["s2"])]
+    assert got == want
+
+
+def test_errors_are_reported_not_thrown(G):
+    GL, _ = H.gen_synth.synth(6, 5, 1)
+    gl, expg, maf = N.prepare_sites(GL)
+    with N.Engine(0) as eng:
+        with pytest.raises(N.NgsldError):
+            eng.scan(N.ScanParams.make(max_kb_dist=0))           # no sites yet
+        bad = maf.copy()
+        bad[2] = 1.5
+        with pytest.raises(N.NgsldError) as ei:
+            eng.set_sites(gl, expg, bad)                          # haplo_freq: "invalid allele frequencies"
+        assert ei.value.code == -4
+        eng.set_sites(gl, expg, maf)
+        with pytest.raises(N.NgsldError):
+            eng.scan(N.ScanParams.make(max_kb_dist=0, rnd_sample=0.0))
+        with pytest.raises(N.NgsldError):
+            eng.pairs([0], [99])
+        assert len(eng.scan(N.ScanParams.make(max_kb_dist=5))) == 0   # no positions: every distance is inf
