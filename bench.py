@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — pairs/s of the pairwise-LD hot path on B200 (driver contract; see DESIGN.md "Measurement").
+
+A *step* is one pass of the hot path over one batch: all pairs of a contiguous slab of first sites
+(≈ --batch-pairs pairs) of the 50 000-SNP x 500-individual all-pairs workload (BASELINE.json configs[2],
+the configuration the metric and the north-star target are quoted on; it fits one GPU).  Batches of
+successive steps are different slabs, and the genotype-likelihood matrix (600 MB) is larger than L2.
+
+  value    — pairs/s with the site table already resident in HBM and results left in HBM
+             (ngsld_scan_device), CUDA events on the library's stream, max over ranks.
+  e2e      — the same batches through the C ABI with HOST buffers: ngsld_set_sites (H2D of the prepared
+             site arrays) + ngsld_scan (binary rows delivered to a host sink), copies inside the timed region.
+  roofline — dominant kernel (the fast EM kernel): algorithmic bytes B_alg * pairs / summed kernel time
+             against the measured HBM peak, plus the FP64 issue fraction that actually bounds the path.
+  cpu_baseline — the unmodified reference binary (oracle/_ref/ngsLD) on all host cores, on a bounded
+             prefix sample of the same workload (same n_ind).
+
+Multi-GPU (torchrun, one rank per GPU): the upper triangle is partitioned into equal-pair-count first-site
+ranges (ngsld_partition); each rank runs its own batches from its own range; no data-path collective.
+`--impl reference` times only the reference CPU implementation (rank 0)."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+METRIC = "snp_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-sites", type=int, default=50000)
+    ap.add_argument("--n-ind", type=int, default=500)
+    ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--batch-pairs", type=int, default=0, help="pairs per step and GPU (0 = auto)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="bit-faithful EM kernel instead of the fast one")
+    return ap.parse_args()
+
+
+def bytes_per_pair(n_ind):
+    """both GL rows + both expected-genotype rows + 7 result doubles."""
+    return 2 * n_ind * 24 + 2 * n_ind * 8 + 56
+
+
+def workload_name(a):
+    return f"synthetic binary GL, {a.n_sites} SNPs x {a.n_ind} ind, all pairs (--max_kb_dist 0)"
+
+
+def make_inputs(a):
+    import gen_synth
+    GL, pos = gen_synth.synth_fast(a.n_sites, a.n_ind, a.seed)
+    return GL, pos
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU implementation on a bounded sample
+def ref_sample_run(GL, pos, n_sub, threads, tmpdir):
+    """Time the reference CLI (or, if it did not travel, the oracle port) on the first n_sub sites."""
+    from oracle import oracle as O  # test infrastructure: the CPU baseline leg is allowed to execute it
+    n_ind = GL.shape[1]
+    n_pairs = n_sub * (n_sub - 1) // 2
+    if O.have_ref():
+        g = os.path.join(tmpdir, f"sample_{n_sub}.glf")
+        if not os.path.exists(g):
+            GL[:n_sub].astype("<f8").tofile(g)
+            with open(g + ".pos", "w") as fh:
+                fh.write("".join(f"chr1\t{p}\n" for p in pos[:n_sub]))
+        t0 = time.perf_counter()
+        O.run_ref(["--geno", g, "--probs", "--n_ind", str(n_ind), "--n_sites", str(n_sub), "--pos", g + ".pos",
+                   "--max_kb_dist", "0"], "/dev/null", n_threads=threads)
+        return n_pairs, time.perf_counter() - t0, "reference"
+    gl, expg, maf = O.preprocess(GL[:n_sub])
+    t0 = time.perf_counter()
+    n, _ = O.run(gl, expg, maf, None, None, extend_out=False, n_threads=threads, out_path="/dev/null")
+    return n, time.perf_counter() - t0, "port"
+
+
+def pick_sample(GL, pos, threads, target_s, tmpdir):
+    """Calibrate on a tiny prefix, then size the sample for ~target_s seconds of CPU wall time."""
+    n_sub = 160
+    for _ in range(4):
+        n, dt, _ = ref_sample_run(GL, pos, n_sub, threads, tmpdir)
+        if dt >= target_s / 4 or n_sub >= GL.shape[0]:
+            break
+        rate = n / max(dt - 0.02, 1e-3)  # minus process start-up
+        nxt = int(min(GL.shape[0], (2 * rate * target_s) ** 0.5))
+        n_sub = max(n_sub + 1, min(nxt, n_sub * 4))
+    n, dt, _ = ref_sample_run(GL, pos, n_sub, threads, tmpdir) if dt < target_s / 4 else (n, dt, None)
+    return int(min(GL.shape[0], max(160, n_sub * (target_s / max(dt, 1e-3)) ** 0.5)))
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    GL, pos = make_inputs(argparse.Namespace(n_sites=min(a.n_sites, 4096), n_ind=a.n_ind, seed=a.seed))
+    with tempfile.TemporaryDirectory() as td:
+        n_sub = pick_sample(GL, pos, threads, max(2.0, a.cpu_seconds / 2), td)
+        times, n_pairs, kind = [], 0, "reference"
+        for k in range(a.warmup + a.steps):
+            n_pairs, dt, kind = ref_sample_run(GL, pos, n_sub, threads, td)
+            if k >= a.warmup:
+                times.append(dt)
+    total = sum(times)
+    v = n_pairs * len(times) / total
+    sample = f"first {n_sub} sites of the workload, all pairs = {n_pairs} pairs per step, --n_threads {threads}"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "n_sites": a.n_sites, "n_ind": a.n_ind},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons of one GPU during the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in ln.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_median": statistics.median(pw) if pw else None}
+
+
+def slab_bounds(n_sites, lo, hi, batch_pairs):
+    """First-site slabs [a, b) inside [lo, hi) of about batch_pairs pairs each (all-pairs triangle)."""
+    per = (n_sites - 1 - np.arange(lo, hi, dtype=np.int64))
+    cum = np.concatenate([[0], np.cumsum(per)])
+    slabs, a = [], 0
+    while a < hi - lo and cum[-1] - cum[a] > 0:
+        b = int(np.searchsorted(cum, cum[a] + batch_pairs, side="left"))
+        b = max(a + 1, min(b, hi - lo))
+        if cum[b] - cum[a] > 0:
+            slabs.append((lo + a, lo + b, int(cum[b] - cum[a])))
+        a = b
+    return slabs
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    import ngsld_b200 as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ngsld_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    GL, pos = make_inputs(a)
+    gl, expg, maf = N.prepare_sites(GL)
+    pos_dist = np.diff(np.concatenate([[0], pos])).astype(np.float64)
+    eng = N.Engine(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_sites(gl, expg, maf)
+    eng.set_positions(pos_dist, None)
+    P = N.ScanParams.make(max_kb_dist=0, strict=int(a.strict))
+    bounds = eng.partition(P, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    fp64_peak = eng.probe_fp64()  # GFLOP/s, measured DFMA issue rate of this GPU
+
+    # batch size: auto = ~1.5 s of device time per step, found with one calibration slab
+    batch = a.batch_pairs
+    if batch <= 0:
+        cal = slab_bounds(a.n_sites, lo, hi, 2_000_000)[0]
+        eng.scan_device(P, cal[0], cal[1])
+        st = eng.scan_device(P, cal[0], cal[1])
+        rate = st["n_pairs"] / (st["ms_device_total"] * 1e-3)
+        batch = int(min(max(rate * (0.25 if a.strict else 1.5), 2_000_000), 64_000_000))
+        if world > 1:
+            t = torch.tensor([batch], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            batch = int(t.item())
+    slabs = slab_bounds(a.n_sites, lo, hi, batch)
+    slabs = [s for s in slabs if s[2] >= batch // 2] or slabs
+    n_steps = a.warmup + a.steps
+
+    def slab(k):
+        return slabs[k % len(slabs)]
+
+    # ---------------- leg 1: HBM-resident ----------------
+    for k in range(a.warmup):
+        eng.scan_device(P, *slab(k)[:2])
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    pairs = launches = passes = 0
+    ms_em = ms_pearson = 0.0
+    for k in range(a.warmup, n_steps):
+        st = eng.scan_device(P, *slab(k)[:2])
+        pairs += st["n_pairs"]
+        launches += st["n_launches"]
+        passes += st["sum_em_passes"]
+        ms_em += st["ms_em"]
+        ms_pearson += st["ms_pearson"]
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_dev = ev0.elapsed_time(ev1)
+
+    # ---------------- leg 2: end to end through the C ABI with host buffers ----------------
+    e2e = None
+    if not a.no_e2e:
+        seen = [0]
+
+        def sink(rows):
+            seen[0] += len(rows)
+
+        def e2e_step(k):
+            eng.set_sites(gl, expg, maf)       # H2D of the prepared site arrays (host buffers)
+            eng.set_positions(pos_dist, None)
+            eng.scan_sink(P, sink, *slab(k)[:2])  # rows D2H into pinned chunks, handed to the sink
+            return eng.stats()
+
+        e2e_step(0)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        seen[0] = 0
+        f0.record(stream)
+        h2d = d2h = 0
+        e_steps = max(1, min(a.steps, 3))
+        for k in range(a.warmup, a.warmup + e_steps):
+            st = e2e_step(k)
+            d2h += st["d2h_bytes"]
+            h2d += st["h2d_bytes"] + gl.nbytes + maf.nbytes * 2 + expg.size * 10  # + site table, x87 terms
+        f1.record(stream)
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+        e2e = {"pairs": seen[0], "ms": ms_e2e, "h2d": h2d / e_steps, "d2h": d2h / e_steps, "steps": e_steps}
+
+    # ---------------- reduce over ranks ----------------
+    vec = torch.tensor([ms_dev, float(pairs), float(launches), float(passes), ms_em, ms_pearson,
+                        e2e["ms"] if e2e else 0.0, float(e2e["pairs"]) if e2e else 0.0], device="cuda",
+                       dtype=torch.float64)
+    mx, sm = vec.clone(), vec.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    mx, sm = mx.tolist(), sm.tolist()
+
+    if rank == 0:
+        ms_max, tot_pairs = mx[0], sm[1]
+        value = tot_pairs / (ms_max * 1e-3)
+        bpp = bytes_per_pair(a.n_ind)
+        # dominant kernel = EM; its per-launch duration from the CUDA events the library records around it
+        # on its own launch stream (rank 0's numbers)
+        em_s = ms_em * 1e-3
+        achieved = pairs * bpp / em_s / 1e9
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            try:
+                peaks = json.load(open(pk))
+            except Exception:
+                peaks = {}
+        hbm_peak = float(peaks.get("hbm_gbs", 0) or 0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        if hbm_peak <= 0:
+            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # FP64 work actually bounding the kernel: 27 FP64 instr + 1 reciprocal (~33 issue slots, 40 flop)
+        # per (individual, EM pass)  [SURVEY.md §8(d)]
+        flop = passes * a.n_ind * 40.0
+        fp64_achieved = flop / em_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": "emfast::em_tile_kernel",
+                    "algorithmic_bytes_per_pair": bpp, "launch_ms_avg": ms_em / max(1, a.steps),
+                    "note": "path is FP64-issue-bound (~%.0f EM passes/pair); see fp64" % (passes / max(1, pairs)),
+                    "fp64": {"achieved_gflops": fp64_achieved, "peak_gflops": fp64_peak,
+                             "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                             "peak_source": "ngsld_probe_fp64 (DFMA issue micro-benchmark, this GPU, this run)",
+                             "flop_per_ind_pass": 40, "mean_em_passes_per_pair": passes / max(1, pairs)}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "n_sites": a.n_sites, "n_ind": a.n_ind,
+                           "pairs_per_step_per_gpu": int(pairs // a.steps), "kernel": "strict" if a.strict else "fast",
+                           "partition": f"equal-pair-count first-site ranges, {world} part(s), no collective",
+                           "l2": "inputs larger than L2 (site table %.0f MB, a different slab each step)" % (gl.nbytes / 1e6)},
+                "gpu_launches": int(sm[2]), "roofline": roofline, "clocks": clocks}
+        if e2e:
+            e_value = sm[7] / (mx[6] * 1e-3)
+            line["e2e"] = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
+                           "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
+                           "api": "ngsld_set_sites + ngsld_set_positions + ngsld_scan(row sink) per step"}
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            with tempfile.TemporaryDirectory() as td:
+                n_sub = pick_sample(GL, pos, threads, a.cpu_seconds, td)
+                n, dt, kind = ref_sample_run(GL, pos, n_sub, threads, td)
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"first {n_sub} sites of the workload, all pairs = {n} pairs, "
+                                              f"--n_threads {threads}, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
