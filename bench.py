@@ -188,6 +188,19 @@ def slab_bounds(n_sites, lo, hi, batch_pairs):
     return slabs
 
 
+def reduce_over_ranks(values, device, world):
+    """(max over ranks, sum over ranks) of a vector of per-rank numbers; the backend is whatever the process
+    group was initialised with (nccl on the GPU box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    vec = torch.tensor(values, device=device, dtype=torch.float64)
+    mx, sm = vec.clone(), vec.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx.tolist(), sm.tolist()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -297,14 +310,8 @@ def main():
         e2e = {"pairs": seen[0], "ms": ms_e2e, "h2d": h2d / e_steps, "d2h": d2h / e_steps, "steps": e_steps}
 
     # ---------------- reduce over ranks ----------------
-    vec = torch.tensor([ms_dev, float(pairs), float(launches), float(passes), ms_em, ms_pearson,
-                        e2e["ms"] if e2e else 0.0, float(e2e["pairs"]) if e2e else 0.0], device="cuda",
-                       dtype=torch.float64)
-    mx, sm = vec.clone(), vec.clone()
-    if world > 1:
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-    mx, sm = mx.tolist(), sm.tolist()
+    mx, sm = reduce_over_ranks([ms_dev, float(pairs), float(launches), float(passes), ms_em, ms_pearson,
+                                e2e["ms"] if e2e else 0.0, float(e2e["pairs"]) if e2e else 0.0], "cuda", world)
 
     if rank == 0:
         ms_max, tot_pairs = mx[0], sm[1]

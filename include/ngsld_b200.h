@@ -91,6 +91,8 @@ typedef int (*ngsld_text_sink)(void *user, const char *bytes, uint64_t n_bytes, 
 
 /* ---- context --------------------------------------------------------------------------------- */
 int ngsld_abi_version(void);
+/* number of usable sm_100 devices (0 if none / no driver); the reference sizes its pool from --n_threads instead. */
+int ngsld_device_count(void);
 /* replaces threadpool_create() (shared/threadpool.c:51-99, call site ngsLD.cpp:154): binds a GPU. */
 int ngsld_create(ngsld_ctx **out, int device);
 /* replaces threadpool_destroy() + the free_ptr block (ngsLD.cpp:197-216). */
@@ -102,6 +104,22 @@ const char *ngsld_last_error(const ngsld_ctx *ctx);
 int ngsld_set_stream(ngsld_ctx *ctx, void *cuda_stream);
 /* cap on rows per device chunk (0 = default); result buffers scale with it. */
 int ngsld_set_chunk_rows(ngsld_ctx *ctx, uint64_t rows);
+
+/* ---- input files (host) --------------------------------------------------------------------------
+ * replaces read_geno() (shared/read_data.cpp:13-116): binary = raw little-endian doubles [n_sites][n_ind][3]
+ * (plain or gz); text = one site per line, blank/tab separated, non-numeric tokens dropped, a short first line is a
+ * header, the LAST n_ind*(probs?3:1) numeric fields are used; genotypes coded -1/0/1/2 when !probs.  cells receives
+ * [n_sites][n_ind][3]; *log_cells = 1 when they are already log-space (text input) — pass it on to
+ * ngsld_prepare_sites(from_log_cells).  Failure: NGSLD_E_IO / NGSLD_E_DATA, and ngsld_last_error(NULL) holds
+ * "[func] message" with the reference's function name and wording. */
+int ngsld_load_geno(const char *path, int is_bin, int probs, int log_scale, uint64_t n_ind, uint64_t n_sites,
+                    double *cells, int *log_cells);
+/* replaces read_dist() + the label fix-up (shared/read_data.cpp:165-218, ngsLD.cpp:119-132): pos_dist[n_sites]
+ * (+inf at a chromosome change) and the labels ("chr:pos...", only the first tab replaced) as one malloc'ed blob of
+ * n_sites NUL-terminated strings, released with ngsld_free(). */
+int ngsld_load_positions(const char *path, int header, uint64_t n_sites, double *pos_dist, char **label_blob,
+                         uint64_t *blob_bytes);
+void ngsld_free(void *p);
 
 /* ---- per-site preparation (host, bit-identical to the reference's glibc path) ---------------- */
 /* replaces the per-cell math of read_geno()'s binary branch (shared/read_data.cpp:28-46), the optional
@@ -128,6 +146,12 @@ void ngsld_scan_defaults(ngsld_scan_params *p);
 int ngsld_scan_count(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, uint64_t *n_rows);
 /* Equal-row-count first-site ranges for n_parts workers: bounds[0..n_parts], bounds[0]=0, bounds[n_parts]=n_sites. */
 int ngsld_partition(ngsld_ctx *ctx, const ngsld_scan_params *p, int n_parts, uint64_t *bounds);
+/* The same two planners without a device (host only; with rnd_sample < 1 they walk every candidate pair's draw, so
+ * use the context versions for large sampled scans): what a multi-process launcher calls to hand each rank its range. */
+int ngsld_plan_count(const double *maf, const double *pos_dist /* NULL = no positions */, uint64_t n_sites,
+                     const ngsld_scan_params *p, uint64_t s1_lo, uint64_t s1_hi, uint64_t *n_rows);
+int ngsld_plan_partition(const double *maf, const double *pos_dist, uint64_t n_sites, const ngsld_scan_params *p,
+                         int n_parts, uint64_t *bounds);
 /* Binary rows to a sink. */
 int ngsld_scan(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_row_sink sink,
                void *user);

@@ -3,7 +3,6 @@
 The binding is deliberately thin: every call goes straight into libngsld_b200.so.  Nothing here computes
 LD on the CPU; if the shared library is absent the import of the library raises, loudly."""
 import ctypes as C
-import gzip
 import os
 
 import numpy as np
@@ -79,6 +78,7 @@ def load_library():
     pu64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
     sig = {
         "ngsld_abi_version": (i32, []),
+        "ngsld_device_count": (i32, []),
         "ngsld_create": (i32, [C.POINTER(vp), i32]),
         "ngsld_destroy": (None, [vp]),
         "ngsld_last_error": (C.c_char_p, [vp]),
@@ -97,6 +97,11 @@ def load_library():
         "ngsld_get_stats": (i32, [vp, C.POINTER(ScanStats)]),
         "ngsld_pairs": (i32, [vp, pu32, pu32, u64, i32, i32, vp]),
         "ngsld_site_seeds": (i32, [u64, u64, pu64]),
+        "ngsld_plan_count": (i32, [pd, vp, u64, C.POINTER(ScanParams), u64, u64, C.POINTER(u64)]),
+        "ngsld_plan_partition": (i32, [pd, vp, u64, C.POINTER(ScanParams), i32, pu64]),
+        "ngsld_load_geno": (i32, [C.c_char_p, i32, i32, i32, u64, u64, pd, C.POINTER(i32)]),
+        "ngsld_load_positions": (i32, [C.c_char_p, i32, u64, pd, C.POINTER(vp), C.POINTER(u64)]),
+        "ngsld_free": (None, [vp]),
         "ngsld_tsv_header": (i32, [i32, C.c_char_p, C.c_size_t]),
         "ngsld_probe_fp64": (i32, [vp, C.POINTER(dbl)]),
     }
@@ -108,11 +113,12 @@ def load_library():
     return L
 
 
-EXPORTED = ["ngsld_abi_version", "ngsld_create", "ngsld_destroy", "ngsld_last_error", "ngsld_set_stream",
+EXPORTED = ["ngsld_abi_version", "ngsld_device_count", "ngsld_create", "ngsld_destroy", "ngsld_last_error", "ngsld_set_stream",
             "ngsld_set_chunk_rows", "ngsld_prepare_sites", "ngsld_set_sites", "ngsld_set_positions",
             "ngsld_scan_defaults", "ngsld_scan_count", "ngsld_partition", "ngsld_scan", "ngsld_scan_into",
             "ngsld_scan_tsv", "ngsld_scan_device", "ngsld_get_stats", "ngsld_pairs", "ngsld_site_seeds",
-            "ngsld_tsv_header", "ngsld_probe_fp64"]
+            "ngsld_tsv_header", "ngsld_probe_fp64", "ngsld_plan_count", "ngsld_plan_partition", "ngsld_load_geno",
+            "ngsld_load_positions", "ngsld_free"]
 
 
 def prepare_sites(raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,
@@ -145,45 +151,67 @@ def tsv_header(extend_out):
     return buf.raw[:n]
 
 
-def read_positions(path, header=False):
-    """--pos / --posH file -> (labels, pos_dist) with the reference's rules (ngsLD.cpp:119-132,
-    shared/read_data.cpp:165-218, shared/gen_func.cpp:238-282): gz or plain; empty and '#' lines skipped; only the
-    first tab of a line becomes ':'; +inf at a chromosome change; adjacent distance must be >= 1."""
-    with open(path, "rb") as fh:
-        magic = fh.read(2)
-    op = gzip.open if magic == b"\x1f\x8b" else open
-    lines = []
-    skip = 1 if header else 0
-    with op(path, "rt") as fh:
-        for ln in fh:
-            if ln.endswith("\n"):
-                ln = ln[:-1]
-            if not ln or ln.startswith("#"):
-                continue
-            if skip:
-                skip -= 1
-                continue
-            lines.append(ln)
-    dist = np.empty(len(lines))
-    prev_chr, prev_pos = None, 0
-    for s, ln in enumerate(lines):
-        f = ln.split("\t")
-        if len(f) < 2:
-            raise ValueError("wrong POS file format!")
-        pos = float(f[1])
-        if pos == 0:
-            raise ValueError("POS file: header line or position 0 found (use --posH for a header)")
-        if prev_chr is None:
-            prev_chr = f[0]
-        if prev_chr == f[0]:
-            dist[s] = pos - prev_pos
-            if dist[s] < 1:
-                raise ValueError("invalid distance between adjacent sites!")
-        else:
-            dist[s] = np.inf
-            prev_chr = f[0]
-        prev_pos = int(pos)
-    return [ln.replace("\t", ":", 1) for ln in lines], dist
+def _global_error():
+    return (load_library().ngsld_last_error(None) or b"").decode()
+
+
+def load_geno(path, n_ind, n_sites, is_bin=None, probs=True, log_scale=False):
+    """ngsld_load_geno: genotype file -> (cells [n_sites, n_ind, 3], log_cells flag).  is_bin defaults to the
+    reference's rule: everything not ending in ".gz" is binary (ngsLD.cpp:45-57)."""
+    if is_bin is None:
+        is_bin = not path.endswith(".gz")
+    cells = np.empty((n_sites, n_ind, 3))
+    lc = C.c_int(0)
+    rc = load_library().ngsld_load_geno(path.encode(), int(is_bin), int(probs or is_bin), int(log_scale), n_ind,
+                                        n_sites, cells, C.byref(lc))
+    if rc != 0:
+        raise NgsldError(rc, _global_error())
+    return cells, bool(lc.value)
+
+
+def read_positions(path, n_sites, header=False):
+    """ngsld_load_positions: --pos / --posH file -> (labels, pos_dist) with the reference's rules (ngsLD.cpp:119-132,
+    shared/read_data.cpp:165-218): gz or plain; empty and '#' lines skipped; only the first tab of a line becomes
+    ':'; +inf at a chromosome change; adjacent distance must be >= 1."""
+    dist = np.empty(n_sites)
+    blob, nbytes = C.c_void_p(), C.c_uint64(0)
+    L = load_library()
+    rc = L.ngsld_load_positions(path.encode(), int(header), n_sites, dist, C.byref(blob), C.byref(nbytes))
+    if rc != 0:
+        raise NgsldError(rc, _global_error())
+    raw = C.string_at(blob, nbytes.value)
+    L.ngsld_free(blob)
+    labels = [x.decode() for x in raw.split(b"\0")[:n_sites]]
+    return labels, dist
+
+
+def plan_count(maf, pos_dist, params, s1_lo=0, s1_hi=None):
+    """ngsld_plan_count: rows first sites [s1_lo, s1_hi) will produce, computed without a device."""
+    maf = np.ascontiguousarray(maf, np.float64)
+    n = C.c_uint64(0)
+    pd_ptr = None
+    if pos_dist is not None:
+        pos_dist = np.ascontiguousarray(pos_dist, np.float64)
+        pd_ptr = pos_dist.ctypes.data_as(C.c_void_p)
+    rc = load_library().ngsld_plan_count(maf, pd_ptr, len(maf), C.byref(params), s1_lo,
+                                         len(maf) if s1_hi is None else s1_hi, C.byref(n))
+    if rc != 0:
+        raise NgsldError(rc, _global_error())
+    return n.value
+
+
+def plan_partition(maf, pos_dist, params, n_parts):
+    """ngsld_plan_partition: equal-row-count first-site ranges for n_parts workers, without a device."""
+    maf = np.ascontiguousarray(maf, np.float64)
+    b = np.zeros(n_parts + 1, np.uint64)
+    pd_ptr = None
+    if pos_dist is not None:
+        pos_dist = np.ascontiguousarray(pos_dist, np.float64)
+        pd_ptr = pos_dist.ctypes.data_as(C.c_void_p)
+    rc = load_library().ngsld_plan_partition(maf, pd_ptr, len(maf), C.byref(params), n_parts, b)
+    if rc != 0:
+        raise NgsldError(rc, _global_error())
+    return b
 
 
 class Engine:

@@ -13,8 +13,10 @@
 
 #include "aux_kernels.cuh"
 #include "em_kernels.cuh"
+#include "em_warp.cuh"
 #include "format.cuh"
-#include "host_prep.h"
+#include "host/host_prep.h"
+#include "host/loader.h"
 
 namespace emfast {
 #define DECL_LPG(n)                              \
@@ -23,6 +25,11 @@ namespace emfast {
 DECL_LPG(4) DECL_LPG(8) DECL_LPG(16) DECL_LPG(32) DECL_LPG(64) DECL_LPG(128) DECL_LPG(256)
 #undef DECL_LPG
 }  // namespace emfast
+
+namespace emwarp {
+extern const WarpVariant warp_variants[];
+extern const int warp_variants_count;
+}  // namespace emwarp
 
 static thread_local std::string g_create_error;
 
@@ -206,11 +213,29 @@ const emfast::EmVariant *pick_variant(uint64_t n_ind) {
 
 // ---- planning -----------------------------------------------------------------------------------
 // Reproduces the control flow of calc_pair_LD's scan (reference ngsLD.cpp:240-282) as index ranges.
-int make_plan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params &P, Plan &pl) {
-  const uint64_t n = c->n_sites;
+struct PlanInput {
+  uint64_t n_sites;
+  const double *maf;
+  bool have_pos;
+  const double *cum;    // exact prefix sums of the finite gaps (valid when have_pos)
+  const uint32_t *seg;  // chromosome segment ids
+};
+
+PlanInput plan_input(const ngsld_ctx *c) {
+  PlanInput in;
+  in.n_sites = c->n_sites;
+  in.maf = c->h_maf.data();
+  in.have_pos = c->have_pos;
+  in.cum = c->h_cum.data();
+  in.seg = c->h_seg.data();
+  return in;
+}
+
+int make_plan(const PlanInput &in, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params &P, Plan &pl) {
+  const uint64_t n = in.n_sites;
   if (s1_hi > n) s1_hi = n;
   if (s1_lo > s1_hi) s1_lo = s1_hi;
-  const std::vector<double> &maf = c->h_maf;
+  const double *maf = in.maf;
   // sites that may appear in a pair at all: !(maf < min_maf)  (ngsLD.cpp:264,270)
   std::vector<uint32_t> kp(n + 1);
   pl.cs.clear();
@@ -235,7 +260,7 @@ int make_plan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_par
     if (e < s1 + 1) e = s1 + 1;
     while (e < n) {
       double dist = INFINITY;
-      if (c->have_pos && c->h_seg[s1] == c->h_seg[e]) dist = c->h_cum[e] - c->h_cum[s1];
+      if (in.have_pos && in.seg[s1] == in.seg[e]) dist = in.cum[e] - in.cum[s1];
       if (P.max_kb_dist > 0 && kb_limit < dist) break;            // ngsLD.cpp:252
       if (P.max_snp_dist > 0 && P.max_snp_dist < e - s1) break;   // ngsLD.cpp:258
       e++;
@@ -254,6 +279,68 @@ int make_plan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_par
     pl.total = acc;
   }
   return NGSLD_OK;
+}
+
+// Exact prefix sums of the inter-site gaps: every finite gap must be a non-negative integer and the total below
+// 2^53, so that cum[s2]-cum[s1] equals the reference's running double sum (ngsLD.cpp:241) bit for bit.  A +inf gap
+// (chromosome change, read_data.cpp:209) starts a new segment.  Returns NULL or the reason for rejection.
+const char *build_cum(const double *pos_dist, uint64_t n, double *cum, uint32_t *seg_out) {
+  double acc = 0;
+  uint32_t seg = 0;
+  for (uint64_t s = 0; s < n; s++) {
+    const double g = pos_dist[s];
+    if (isinf(g) && g > 0) {
+      if (s > 0) seg++;
+    } else {
+      if (!(g >= 0) || g != floor(g)) return "inter-site distances must be non-negative integers or +inf";
+      if (s > 0) acc += g;  // pos_dist[0] (distance from the origin) never enters a pair distance
+      if (acc > 9007199254740992.0) return "positions exceed 2^53";
+    }
+    cum[s] = acc;
+    seg_out[s] = seg;
+  }
+  return nullptr;
+}
+
+// Host-side kept-pair counts of a sampled scan (reference ngsLD.cpp:277 with the per-site taus streams of
+// ngsLD.cpp:165-166).  O(candidate pairs): used only by the device-free planning entry points; scans and
+// ngsld_partition count on the device (aux::taus_sample_kernel).
+void host_sample_counts(const Plan &pl, const ngsld_scan_params &P, uint64_t n_sites, std::vector<unsigned long long> &counts) {
+  std::vector<uint64_t> seeds(n_sites);
+  hostprep::site_seeds(P.seed, n_sites, seeds.data());
+  counts.assign(pl.c_hi - pl.c_lo, 0);
+  for (uint32_t c1 = pl.c_lo; c1 < pl.c_hi; c1++) {
+    hostprep::TausStream g(seeds[pl.cs[c1]]);
+    unsigned long long kept = 0;
+    for (uint32_t c2 = c1 + 1; c2 < pl.cw_end[c1]; c2++)
+      if (!(g.uniform() > P.rnd_sample)) kept++;
+    counts[c1 - pl.c_lo] = kept;
+  }
+}
+
+void finish_sampled_plan(Plan &pl, const std::vector<unsigned long long> &counts) {
+  unsigned long long acc = 0;
+  for (uint32_t k = 0; k < pl.n_compact; k++) {
+    pl.row_off[k] = acc;
+    if (k >= pl.c_lo && k < pl.c_hi) acc += counts[k - pl.c_lo];
+  }
+  pl.row_off[pl.n_compact] = acc;
+  pl.total = acc;
+}
+
+// Equal-row-count first-site boundaries from a whole-range plan.
+void bounds_from_plan(const Plan &pl, uint64_t n_sites, int n_parts, uint64_t *bounds) {
+  bounds[0] = 0;
+  for (int k = 1; k < n_parts; k++) {
+    const unsigned long long target = (unsigned long long)((long double)pl.total * k / n_parts);
+    // first compact site whose rows start at or after the target
+    auto it = std::lower_bound(pl.row_off.begin(), pl.row_off.begin() + pl.n_compact, target);
+    const size_t cidx = it - pl.row_off.begin();
+    uint64_t s = cidx < pl.n_compact ? pl.cs[cidx] : n_sites;
+    if (s < bounds[k - 1]) s = bounds[k - 1];
+    bounds[k] = s;
+  }
+  bounds[n_parts] = n_sites;
 }
 
 int ensure_plan_buffers(ngsld_ctx *c, size_t n_compact) {
@@ -302,13 +389,7 @@ int upload_plan(ngsld_ctx *c, Plan &pl, const ngsld_scan_params &P) {
       CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
       c->stats.d2h_bytes += span * 8ull;
     }
-    unsigned long long acc = 0;
-    for (uint32_t k = 0; k < pl.n_compact; k++) {
-      pl.row_off[k] = acc;
-      if (k >= pl.c_lo && k < pl.c_hi) acc += counts[k - pl.c_lo];
-    }
-    pl.row_off[pl.n_compact] = acc;
-    pl.total = acc;
+    finish_sampled_plan(pl, counts);
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->d_row_off, pl.row_off.data(), ((size_t)pl.n_compact + 1) * 8, cudaMemcpyHostToDevice, c->s_main));
   c->stats.h2d_bytes += ((uint64_t)pl.n_compact + 1) * 8;
@@ -325,13 +406,56 @@ uint32_t row_owner(const Plan &pl, unsigned long long g) {
 
 struct EmChoice {
   const emfast::EmVariant *v = nullptr;
+  const emwarp::WarpVariant *w = nullptr;  // warp-per-pair kernel (preferred where it applies)
+  size_t warp_smem = 0;
+  int blocks_warp = 0;
   bool tile = false;
   uint32_t TA = 0, TB = 0;
   size_t dyn_smem = 0;
   int blocks_list = 0, blocks_tile = 0;
 };
 
+// Warp-per-pair kernel: R registers-resident individuals per lane, the rest of the rows in a warp-private
+// shared-memory slice.  Used when at least 3 CTAs (12 warps) fit per SM.
+int choose_warp(ngsld_ctx *c, EmChoice &ch) {
+  const char *path = getenv("NGSLD_EM_PATH");  // "warp" | "list" | "tile" for experiments
+  if (path && strcmp(path, "warp") != 0) return NGSLD_OK;
+  const uint64_t min_ind = path ? 1 : 160;  // below: the sub-warp group kernels waste fewer lanes
+  if (c->n_ind < min_ind) return NGSLD_OK;
+  int r = (int)std::min<uint64_t>(8, (c->n_ind + 31) / 32);
+  const char *force = getenv("NGSLD_WARP_R");
+  if (force && atoi(force) >= 1 && atoi(force) <= 8) r = atoi(force);
+  const emwarp::WarpVariant *w = &emwarp::warp_variants[r - 1];
+  const size_t tail_pad = c->n_pad > 32u * (size_t)r ? c->n_pad - 32u * (size_t)r : 0;
+  const size_t smem = emwarp::WARPS_PER_CTA * 2 * tail_pad * 24;
+  if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
+  int occ = 0;
+  for (const void *fn : {w->fn, w->fn_ign}) {
+    CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, emwarp::CTA_THREADS, smem));
+  }
+  if (occ < 3 && !path) return NGSLD_OK;
+  ch.w = w;
+  ch.warp_smem = smem;
+  ch.blocks_warp = std::max(1, occ) * c->sm_count;
+  return NGSLD_OK;
+}
+
+int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss) {
+  SiteTable Tt = T;
+  PairChunk Cc = C;
+  DevCounters *ctr = c->d_ctr;
+  void *args[] = {&Tt, &Cc, &ctr};
+  const unsigned long long want = (C.n_pairs + emwarp::WARPS_PER_CTA - 1) / emwarp::WARPS_PER_CTA;
+  const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_warp);
+  CUDA_TRY(c, cudaLaunchKernel(ignore_miss ? ch.w->fn_ign : ch.w->fn, dim3(blocks), dim3(emwarp::CTA_THREADS), args,
+                               ch.warp_smem, c->s_main));
+  return NGSLD_OK;
+}
+
 int choose_em(ngsld_ctx *c, const Plan &pl, EmChoice &ch) {
+  int rcw = choose_warp(c, ch);
+  if (rcw) return rcw;
   ch.v = pick_variant(c->n_ind);
   if (!ch.v) return NGSLD_OK;  // falls back to the strict kernel (n_ind > 2048)
   int occ = 0;
@@ -411,9 +535,12 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   // EM
   CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
   CUDA_TRY(c, cudaEventRecord(b.ev_em0, c->s_main));
-  if (P.strict || ch.v == nullptr) {
+  if (P.strict || (ch.v == nullptr && ch.w == nullptr)) {
     const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
     aux::em_strict_kernel<<<sb, 128, 0, c->s_main>>>(T, C, P.ignore_miss_data, c->d_ctr);
+  } else if (ch.w) {
+    int rcw = launch_warp(c, ch, T, C, P.ignore_miss_data);
+    if (rcw) return rcw;
   } else if (ch.tile) {
     emfast::TileArgs A;
     A.tiles = c->d_tiles + t0;
@@ -526,7 +653,7 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   memset(&c->stats, 0, sizeof c->stats);
   const double t_plan0 = now_ms();
   Plan pl;
-  int rc = make_plan(c, s1_lo, s1_hi, P, pl);
+  int rc = make_plan(plan_input(c), s1_lo, s1_hi, P, pl);
   if (rc) return rc;
   rc = upload_plan(c, pl, P);
   if (rc) return rc;
@@ -548,7 +675,7 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   }
   uint64_t chunk = std::min<unsigned long long>(c->chunk_rows, pl.total);
   if (d.mode == MODE_TEXT) chunk = std::min<uint64_t>(chunk, 1ull << 20);
-  const bool use_tiles = ch.tile && ch.v && !P.strict;
+  const bool use_tiles = ch.tile && ch.v && !ch.w && !P.strict;
   std::vector<uint2> tiles;
   std::vector<size_t> block_off;
   if (use_tiles) {
@@ -628,6 +755,12 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
 extern "C" {
 
 int ngsld_abi_version(void) { return NGSLD_ABI_VERSION; }
+
+int ngsld_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
 
 int ngsld_create(ngsld_ctx **out, int device) {
   if (!out) return NGSLD_E_INVALID;
@@ -799,20 +932,8 @@ int ngsld_set_positions(ngsld_ctx *c, const double *pos_dist, const char *const 
   if (pos_dist) {
     // exact prefix sums: every finite gap must be a non-negative integer and the total below 2^53, so that
     // cum[s2]-cum[s1] equals the reference's running double sum (ngsLD.cpp:241) bit for bit
-    double acc = 0;
-    uint32_t seg = 0;
-    for (uint64_t s = 0; s < n; s++) {
-      const double g = pos_dist[s];
-      if (isinf(g) && g > 0) {
-        if (s > 0) seg++;
-      } else {
-        if (!(g >= 0) || g != floor(g)) return fail(c, NGSLD_E_DATA, "inter-site distances must be non-negative integers or +inf");
-        if (s > 0) acc += g;  // pos_dist[0] (distance from the origin) never enters a pair distance
-        if (acc > 9007199254740992.0) return fail(c, NGSLD_E_DATA, "positions exceed 2^53");
-      }
-      c->h_cum[s] = acc;
-      c->h_seg[s] = seg;
-    }
+    const char *why = build_cum(pos_dist, n, c->h_cum.data(), c->h_seg.data());
+    if (why) return fail(c, NGSLD_E_DATA, why);
     dfree(c->d_cum);
     CUDA_TRY(c, cudaMalloc(&c->d_cum, n * sizeof(double)));
     CUDA_TRY(c, cudaMemcpy(c->d_cum, c->h_cum.data(), n * 8, cudaMemcpyHostToDevice));
@@ -863,7 +984,7 @@ int ngsld_scan_count(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_s
   if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
   CUDA_TRY(c, cudaSetDevice(c->device));
   Plan pl;
-  int rc = make_plan(c, s1_lo, s1_hi, *p, pl);
+  int rc = make_plan(plan_input(c), s1_lo, s1_hi, *p, pl);
   if (rc) return rc;
   if (pl.sampled) {
     rc = upload_plan(c, pl, *p);
@@ -878,25 +999,118 @@ int ngsld_partition(ngsld_ctx *c, const ngsld_scan_params *p, int n_parts, uint6
   if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
   CUDA_TRY(c, cudaSetDevice(c->device));
   Plan pl;
-  int rc = make_plan(c, 0, c->n_sites, *p, pl);
+  int rc = make_plan(plan_input(c), 0, c->n_sites, *p, pl);
   if (rc) return rc;
   if (pl.sampled) {
     rc = upload_plan(c, pl, *p);
     if (rc) return rc;
   }
-  bounds[0] = 0;
-  for (int k = 1; k < n_parts; k++) {
-    const unsigned long long target = (unsigned long long)((long double)pl.total * k / n_parts);
-    // first compact site whose rows start at or after the target
-    auto it = std::lower_bound(pl.row_off.begin(), pl.row_off.begin() + pl.n_compact, target);
-    const size_t cidx = it - pl.row_off.begin();
-    uint64_t s = cidx < pl.n_compact ? pl.cs[cidx] : c->n_sites;
-    if (s < bounds[k - 1]) s = bounds[k - 1];
-    bounds[k] = s;
-  }
-  bounds[n_parts] = c->n_sites;
+  bounds_from_plan(pl, c->n_sites, n_parts, bounds);
   return NGSLD_OK;
 }
+
+// ---- device-free planning and input files -------------------------------------------------------
+namespace {
+int host_plan(const double *maf, const double *pos_dist, uint64_t n_sites, const ngsld_scan_params *p, uint64_t s1_lo,
+              uint64_t s1_hi, Plan &pl) {
+  if (!maf || !p || n_sites == 0) {
+    g_create_error = "null or empty planning input";
+    return NGSLD_E_INVALID;
+  }
+  if (!(p->rnd_sample > 0) || p->rnd_sample > 1) {
+    g_create_error = "proportion of comparisons to sample must be in ]0,1]!";
+    return NGSLD_E_INVALID;
+  }
+  std::vector<double> cum(n_sites, 0.0);
+  std::vector<uint32_t> seg(n_sites, 0);
+  if (pos_dist) {
+    const char *why = build_cum(pos_dist, n_sites, cum.data(), seg.data());
+    if (why) {
+      g_create_error = why;
+      return NGSLD_E_DATA;
+    }
+  }
+  PlanInput in;
+  in.n_sites = n_sites;
+  in.maf = maf;
+  in.have_pos = pos_dist != nullptr;
+  in.cum = cum.data();
+  in.seg = seg.data();
+  int rc = make_plan(in, s1_lo, s1_hi, *p, pl);
+  if (rc) return rc;
+  if (pl.sampled) {
+    std::vector<unsigned long long> counts;
+    host_sample_counts(pl, *p, n_sites, counts);
+    finish_sampled_plan(pl, counts);
+  }
+  return NGSLD_OK;
+}
+}  // namespace
+
+int ngsld_plan_count(const double *maf, const double *pos_dist, uint64_t n_sites, const ngsld_scan_params *p,
+                     uint64_t s1_lo, uint64_t s1_hi, uint64_t *n_rows) {
+  if (!n_rows) return NGSLD_E_INVALID;
+  Plan pl;
+  int rc = host_plan(maf, pos_dist, n_sites, p, s1_lo, s1_hi, pl);
+  if (rc) return rc;
+  *n_rows = pl.total;
+  return NGSLD_OK;
+}
+
+int ngsld_plan_partition(const double *maf, const double *pos_dist, uint64_t n_sites, const ngsld_scan_params *p,
+                         int n_parts, uint64_t *bounds) {
+  if (!bounds || n_parts < 1) return NGSLD_E_INVALID;
+  Plan pl;
+  int rc = host_plan(maf, pos_dist, n_sites, p, 0, n_sites, pl);
+  if (rc) return rc;
+  bounds_from_plan(pl, n_sites, n_parts, bounds);
+  return NGSLD_OK;
+}
+
+int ngsld_load_geno(const char *path, int is_bin, int probs, int log_scale, uint64_t n_ind, uint64_t n_sites,
+                    double *cells, int *log_cells) {
+  if (!path || !cells || !log_cells || n_ind == 0 || n_sites == 0) {
+    g_create_error = "[read_geno] null or empty arguments";
+    return NGSLD_E_INVALID;
+  }
+  bool lc = false;
+  const loader::Failure f = loader::read_geno(path, is_bin != 0, probs != 0, log_scale != 0, n_ind, n_sites, cells, &lc);
+  *log_cells = lc ? 1 : 0;
+  if (f) {
+    g_create_error = std::string("[") + f.func + "] " + f.msg;
+    return f.io ? NGSLD_E_IO : NGSLD_E_DATA;
+  }
+  return NGSLD_OK;
+}
+
+int ngsld_load_positions(const char *path, int header, uint64_t n_sites, double *pos_dist, char **label_blob,
+                         uint64_t *blob_bytes) {
+  if (!path || !pos_dist || !label_blob || n_sites == 0) {
+    g_create_error = "[read_dist] null or empty arguments";
+    return NGSLD_E_INVALID;
+  }
+  *label_blob = nullptr;
+  std::vector<std::string> labels;
+  const loader::Failure f = loader::read_positions(path, header != 0, n_sites, labels, pos_dist);
+  if (f) {
+    g_create_error = std::string("[") + f.func + "] " + f.msg;
+    return f.io ? NGSLD_E_IO : NGSLD_E_DATA;
+  }
+  size_t total = 0;
+  for (auto &l : labels) total += l.size() + 1;
+  char *blob = (char *)malloc(total ? total : 1);
+  if (!blob) return NGSLD_E_NOMEM;
+  size_t o = 0;
+  for (auto &l : labels) {
+    memcpy(blob + o, l.c_str(), l.size() + 1);
+    o += l.size() + 1;
+  }
+  *label_blob = blob;
+  if (blob_bytes) *blob_bytes = total;
+  return NGSLD_OK;
+}
+
+void ngsld_free(void *p) { free(p); }
 
 int ngsld_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_row_sink sink, void *user) {
   Delivery d;
@@ -1002,8 +1216,11 @@ int ngsld_pairs(ngsld_ctx *c, const uint32_t *s1, const uint32_t *s2, uint64_t n
     const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
     aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C);
     CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
-    if (strict || !ch.v) {
+    if (strict || (!ch.v && !ch.w)) {
       aux::em_strict_kernel<<<pb, 128, 0, c->s_main>>>(T, C, ignore_miss_data, c->d_ctr);
+    } else if (ch.w) {
+      int rcw = launch_warp(c, ch, T, C, ignore_miss_data);
+      if (rcw) return rcw;
     } else {
       int ign = ignore_miss_data;
       SiteTable Tt = T;

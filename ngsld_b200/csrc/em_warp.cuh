@@ -1,0 +1,244 @@
+// Warp-per-pair fast EM (replaces haplo_freq + pair_freq_iter, reference shared/gen_func.cpp:1027-1119)
+// for sample sizes of a few hundred individuals.
+//
+// One warp owns one site pair for its whole EM; warps never synchronise with each other.  Each lane
+// keeps R individuals of the pair in registers (their six genotype likelihoods p[3], q[3]); the rest of
+// the two rows (individuals [32R, n_ind)) is staged ONCE per pair into a warp-private shared-memory
+// slice by two TMA bulk copies and re-read from there on every pass with conflict-free 128-bit loads
+// (a lane owns two adjacent individuals = 48 contiguous bytes of each row).  Registers + shared memory
+// together hold the pair, so the <=100 passes never touch L2/HBM, and the register footprint stays low
+// enough for three resident warps per scheduler -- what the FP64 pipe needs to stay busy (the
+// register-only kernels of em_fast.cuh run two).
+//
+// Per pass and individual (27 FP64 + 1 MUFU):
+//     u0 = f0 q0 + f1 q1   u1 = f2 q0 + f3 q1   v0 = f0 q1 + f1 q2   v1 = f2 q1 + f3 q2        (8)
+//     i0 = p0 u0 + p1 u1   i1 = p0 v0 + p1 v1   i2 = p1 u0 + p2 u1   i3 = p1 v0 + p2 v1        (8)
+//     s  = f0 i0 + f1 i1 + f2 i2 + f3 i3   == the reference's `sum`                             (4)
+//     a_k += i_k / s                                                                       (3 + 4)
+// and per pass once: A_k = sum over lanes of a_k (transposing butterfly: 6 adds instead of 20),
+// f_k <- f_k A_k / n_used.  f_k i_k is the reference's tmp_k / 2 and its M-step is ff/(2x), so this is
+// the same fixed-point iteration; results agree with the bit-faithful kernel to ~1e-15 at equal nIter.
+#pragma once
+#include "common.cuh"
+#include "em_fast.cuh"     // rcp_fast
+#include "em_kernels.cuh"  // mbarrier / TMA helpers
+
+namespace emwarp {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
+
+struct Ind {
+  double p0, p1, p2, q0, q1, q2;
+};
+
+// one individual's E-step contribution
+__device__ __forceinline__ void estep(const double f0, const double f1, const double f2, const double f3, const Ind &g,
+                                      double &i0, double &i1, double &i2, double &i3, double &s) {
+  const double u0 = __fma_rn(f1, g.q1, f0 * g.q0);
+  const double u1 = __fma_rn(f3, g.q1, f2 * g.q0);
+  const double v0 = __fma_rn(f1, g.q2, f0 * g.q1);
+  const double v1 = __fma_rn(f3, g.q2, f2 * g.q1);
+  i0 = __fma_rn(g.p1, u1, g.p0 * u0);
+  i1 = __fma_rn(g.p1, v1, g.p0 * v0);
+  i2 = __fma_rn(g.p2, u1, g.p1 * u0);
+  i3 = __fma_rn(g.p2, v1, g.p1 * v0);
+  s = __fma_rn(f3, i3, __fma_rn(f2, i2, __fma_rn(f1, i1, f0 * i0)));
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ double shfl_idx_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+// Sums a0..a3 over the 32 lanes; every lane receives the same four totals.
+__device__ __forceinline__ void warp_sum4(double &a0, double &a1, double &a2, double &a3, int lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  double x0 = hi16 ? a2 : a0, x1 = hi16 ? a3 : a1;
+  const double y0 = hi16 ? a0 : a2, y1 = hi16 ? a1 : a3;
+  x0 += shfl_xor_d(y0, 16);
+  x1 += shfl_xor_d(y1, 16);
+  double z = hi8 ? x1 : x0;
+  const double w = hi8 ? x0 : x1;
+  z += shfl_xor_d(w, 8);
+  z += shfl_xor_d(z, 4);
+  z += shfl_xor_d(z, 2);
+  z += shfl_xor_d(z, 1);
+  a0 = shfl_idx_d(z, 0);
+  a1 = shfl_idx_d(z, 8);
+  a2 = shfl_idx_d(z, 16);
+  a3 = shfl_idx_d(z, 24);
+}
+
+// R    individuals per lane held in registers (individuals lane + 32 r, r < R)
+// IGN  --ignore_miss_data: individuals whose likelihoods are flat at either site are left out
+// Dynamic shared memory: WARPS_PER_CTA * 2 * tail_bytes, tail_bytes = (n_pad - 32 R) * 24 (0 if n_pad <= 32 R).
+template <int R, bool IGN>
+__global__ void __launch_bounds__(CTA_THREADS, (R <= 4 ? 4 : 3)) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ __align__(8) uint64_t bars[WARPS_PER_CTA];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_ind = T.n_ind;
+  const uint32_t reg_n = n_ind < 32u * R ? n_ind : 32u * R;       // individuals covered by registers
+  const uint32_t tail_n = n_ind - reg_n;                          // individuals streamed from shared memory
+  const uint32_t tail_pad = T.n_pad > 32u * R ? T.n_pad - 32u * R : 0u;
+  const uint32_t tail_bytes = tail_pad * 24u;
+  const size_t row_doubles = (size_t)T.n_pad * 3;
+  const double *tail_a = reinterpret_cast<const double *>(dyn_smem + (size_t)warp * 2 * tail_bytes);
+  const double *tail_b = tail_a + (size_t)tail_pad * 3;
+  uint64_t *bar = &bars[warp];
+  if (lane == 0) emfast::mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t phase = 0;
+  unsigned long long my_passes = 0;
+  const uint32_t n_iter_tail = (tail_n + 63u) / 64u;  // each lane handles individuals 2*lane + 64*j (+1)
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(&ctr->next_pair, 1ull);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= C.n_pairs) break;
+    const uint32_t s1 = C.s1[idx], s2 = C.s2[idx];
+    const double *row_a = T.gl + (size_t)s1 * row_doubles, *row_b = T.gl + (size_t)s2 * row_doubles;
+
+    // ---- stage the row tails (async proxy) while the register part is loaded ----
+    if (tail_bytes) {
+      __syncwarp();  // every lane is done reading the previous pair's tails
+      if (lane == 0) {
+        emfast::mbar_expect_tx(bar, 2 * tail_bytes);
+        emfast::tma_row_load(const_cast<double *>(tail_a), row_a + (size_t)32 * R * 3, tail_bytes, bar);
+        emfast::tma_row_load(const_cast<double *>(tail_b), row_b + (size_t)32 * R * 3, tail_bytes, bar);
+      }
+    }
+    Ind g[R];
+    uint32_t rmask = 0;  // bit r: register individual r takes part
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t i = (uint32_t)lane + 32u * r;
+      bool ok = i < reg_n;
+      g[r].p0 = g[r].p1 = g[r].p2 = g[r].q0 = g[r].q1 = g[r].q2 = 0.0;
+      if (ok) {
+        const double *pa = row_a + 3 * (size_t)i, *pb = row_b + 3 * (size_t)i;
+        g[r].p0 = pa[0]; g[r].p1 = pa[1]; g[r].p2 = pa[2];
+        g[r].q0 = pb[0]; g[r].q1 = pb[1]; g[r].q2 = pb[2];
+        if (IGN && (gl_missing(g[r].p0, g[r].p1, g[r].p2) || gl_missing(g[r].q0, g[r].q1, g[r].q2))) ok = false;
+      }
+      rmask |= (ok ? 1u : 0u) << r;
+    }
+    const bool reg_full = reg_n == 32u * R;  // warp-uniform: no register slot is out of range
+    if (tail_bytes) {
+      emfast::mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+    // tail mask (only with IGN): bit 2j / 2j+1 = the lane's two individuals of tail iteration j take part
+    unsigned long long tmask = ~0ull;
+    uint32_t n_used = n_ind;
+    if (IGN) {
+      tmask = 0;
+      for (uint32_t j = 0; j < n_iter_tail; j++) {
+        const uint32_t i0 = 2u * lane + 64u * j;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const uint32_t i = i0 + e;
+          if (i < tail_n) {
+            const double *pa = tail_a + 3 * (size_t)i, *pb = tail_b + 3 * (size_t)i;
+            if (!(gl_missing(pa[0], pa[1], pa[2]) || gl_missing(pb[0], pb[1], pb[2]))) tmask |= 1ull << (2 * j + e);
+          }
+        }
+      }
+      uint32_t cnt = __popc(rmask) + __popcll(tmask);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      n_used = cnt;
+    }
+    const double inv_x = __ddiv_rn(1.0, (double)n_used);
+    const double m1 = T.maf[s1], m2 = T.maf[s2];  // haplo_freq start point, gen_func.cpp:1034-1037
+    double f0 = __dmul_rn(__dsub_rn(1.0, m1), __dsub_rn(1.0, m2));
+    double f1 = __dmul_rn(__dsub_rn(1.0, m1), m2);
+    double f2 = __dmul_rn(m1, __dsub_rn(1.0, m2));
+    double f3 = __dmul_rn(m1, m2);
+    double A0 = 0, A1 = 0, A2 = 0, A3 = 0;
+    uint32_t it = 0;
+    bool conv = false;
+
+    for (;;) {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      // ---- register-resident individuals ----
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        double i0, i1, i2, i3, s;
+        estep(f0, f1, f2, f3, g[r], i0, i1, i2, i3, s);
+        double inv = emfast::rcp_fast(s);
+        if (IGN || !reg_full)
+          if (!((rmask >> r) & 1u)) inv = 0.0;
+        a0 = __fma_rn(i0, inv, a0);
+        a1 = __fma_rn(i1, inv, a1);
+        a2 = __fma_rn(i2, inv, a2);
+        a3 = __fma_rn(i3, inv, a3);
+      }
+      // ---- individuals streamed from the warp's shared-memory slice ----
+#pragma unroll 2
+      for (uint32_t j = 0; j < n_iter_tail; j++) {
+        const uint32_t i0x = 2u * lane + 64u * j;
+        if (i0x < tail_n) {
+          const double2 *pa = reinterpret_cast<const double2 *>(tail_a + 3 * (size_t)i0x);
+          const double2 *pb = reinterpret_cast<const double2 *>(tail_b + 3 * (size_t)i0x);
+          const double2 pa0 = pa[0], pa1 = pa[1], pa2 = pa[2];
+          const double2 pb0 = pb[0], pb1 = pb[1], pb2 = pb[2];
+          Ind ga, gb;
+          ga.p0 = pa0.x; ga.p1 = pa0.y; ga.p2 = pa1.x; gb.p0 = pa1.y; gb.p1 = pa2.x; gb.p2 = pa2.y;
+          ga.q0 = pb0.x; ga.q1 = pb0.y; ga.q2 = pb1.x; gb.q0 = pb1.y; gb.q1 = pb2.x; gb.q2 = pb2.y;
+          double i0, i1, i2, i3, s, k0, k1, k2, k3, t;
+          estep(f0, f1, f2, f3, ga, i0, i1, i2, i3, s);
+          estep(f0, f1, f2, f3, gb, k0, k1, k2, k3, t);
+          double inv_a = emfast::rcp_fast(s), inv_b = emfast::rcp_fast(t);
+          if (IGN) {
+            if (!((tmask >> (2 * j)) & 1ull)) inv_a = 0.0;
+            if (!((tmask >> (2 * j + 1)) & 1ull)) inv_b = 0.0;
+          } else if (i0x + 1 >= tail_n) {
+            inv_b = 0.0;  // odd sample size: the pad slot
+          }
+          a0 = __fma_rn(i0, inv_a, a0);
+          a1 = __fma_rn(i1, inv_a, a1);
+          a2 = __fma_rn(i2, inv_a, a2);
+          a3 = __fma_rn(i3, inv_a, a3);
+          a0 = __fma_rn(k0, inv_b, a0);
+          a1 = __fma_rn(k1, inv_b, a1);
+          a2 = __fma_rn(k2, inv_b, a2);
+          a3 = __fma_rn(k3, inv_b, a3);
+        }
+      }
+      warp_sum4(a0, a1, a2, a3, lane);
+      // ---- M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5) ----
+      A0 = f0 * a0; A1 = f1 * a1; A2 = f2 * a2; A3 = f3 * a3;
+      const double n0 = A0 * inv_x, n1 = A1 * inv_x, n2 = A2 * inv_x, n3 = A3 * inv_x;
+      double eps = fabs(n0 - f0);
+      eps = fmax(eps, fabs(n1 - f1));
+      eps = fmax(eps, fabs(n2 - f2));
+      eps = fmax(eps, fabs(n3 - f3));
+      // fmax drops NaNs; the reference's `if (d > eps)` chain also never lets a NaN difference raise eps
+      f0 = n0; f1 = n1; f2 = n2; f3 = n3;
+      conv = eps < NGSLD_EPS;
+      if (conv || it == NGSLD_ITER_MAX - 1) break;
+      it++;
+    }
+    if (lane == 0) {
+      // Output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113): true divisions and the
+      // sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes.
+      const double xd = (double)n_used;
+      double gq[4] = {__ddiv_rn(A0, xd), __ddiv_rn(A1, xd), __ddiv_rn(A2, xd), __ddiv_rn(A3, xd)};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));
+      derive_and_store(C.rows + idx, gq, conv ? it : (uint32_t)NGSLD_ITER_MAX, n_used);
+      my_passes += it + 1;
+    }
+  }
+  if (lane == 0 && my_passes) atomicAdd(&ctr->em_passes, my_passes);
+}
+
+struct WarpVariant {
+  int r;
+  const void *fn, *fn_ign;
+};
+
+}  // namespace emwarp

@@ -182,28 +182,17 @@ void pearson_site_terms(const double *expg, uint64_t n_sites, uint64_t n_ind, ui
   });
 }
 
-// gsl_rng_taus (GSL rng/taus.c) -- host copy used only to seed the per-site streams
-struct Taus {
-  uint32_t a, b, c;
-  uint32_t get() {
-    a = ((a & 4294967294u) << 12) ^ (((a << 13) ^ a) >> 19);
-    b = ((b & 4294967288u) << 4) ^ (((b << 2) ^ b) >> 25);
-    c = ((c & 4294967280u) << 17) ^ (((c << 3) ^ c) >> 11);
-    return a ^ b ^ c;
-  }
-  void set(uint64_t seed) {
-    if (seed == 0) seed = 1;
-    a = (uint32_t)(69069ull * seed);
-    b = (uint32_t)(69069ull * a);
-    c = (uint32_t)(69069ull * b);
-    for (int k = 0; k < 6; k++) get();
-  }
-};
+TausStream::TausStream(uint64_t seed) {
+  if (seed == 0) seed = 1;
+  a = (uint32_t)(69069ull * seed);
+  b = (uint32_t)(69069ull * a);
+  c = (uint32_t)(69069ull * b);
+  for (int k = 0; k < 6; k++) get();
+}
 
 // reference ngsLD.cpp:69-70,165-166: seed_s = (unsigned long)(0 + uniform(master) * (1e15 - 0))
 void site_seeds(uint64_t seed, uint64_t n_sites, uint64_t *out) {
-  Taus master;
-  master.set(seed);
+  TausStream master(seed);
   const uint64_t lo = 0, hi = (uint64_t)kBig;
   for (uint64_t s = 0; s < n_sites; s++) {
     const double u = master.get() / 4294967296.0;

@@ -18,4 +18,17 @@ void pearson_site_terms(const double *expg, uint64_t n_sites, uint64_t n_ind, ui
                         uint64_t *dx_sig, uint16_t *dx_se, double *q);
 void site_seeds(uint64_t seed, uint64_t n_sites, uint64_t *out);
 
+// gsl_rng_taus (GSL rng/taus.c) seeded like gsl_rng_set; uniform() = get()/2^32 as gsl_rng_uniform.
+struct TausStream {
+  uint32_t a, b, c;
+  explicit TausStream(uint64_t seed);
+  uint32_t get() {
+    a = ((a & 4294967294u) << 12) ^ (((a << 13) ^ a) >> 19);
+    b = ((b & 4294967288u) << 4) ^ (((b << 2) ^ b) >> 25);
+    c = ((c & 4294967280u) << 17) ^ (((c << 3) ^ c) >> 11);
+    return a ^ b ^ c;
+  }
+  double uniform() { return get() / 4294967296.0; }
+};
+
 }  // namespace hostprep
