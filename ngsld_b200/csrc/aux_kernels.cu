@@ -91,9 +91,18 @@ __global__ void __launch_bounds__(128) em_strict_kernel(SiteTable T, PairChunk C
 //     sum_cross = sum_{i>=1} fl80( fl80(da_i * db_i) * (long double)(i/(i+1.0)) )   (in order)
 //     r = fl80( sum_cross / (long double)(qa*qb) ),  r2 = (double)r * (double)r.
 // One thread per pair; the sum is inherently sequential.
-__global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C) {
-  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < C.n_pairs;
-       p += (unsigned long long)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
+  // Persistent: each warp repeatedly claims 32 consecutive pairs.  The launch is sized to ONE small CTA per SM when
+  // the warp-per-pair EM kernel runs beside it: that kernel is bound by the FP64 pipe and leaves integer issue slots
+  // and 10 K registers per SM free, so this integer-only kernel rides along for free instead of running before it.
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->next_pearson, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= C.n_pairs) break;
+    const unsigned long long p = base + lane;
+    if (p >= C.n_pairs) continue;
     const uint32_t s1 = C.s1[p], s2 = C.s2[p];
     const uint64_t *ma = T.dx_sig + (size_t)s1 * T.n_pad, *mb = T.dx_sig + (size_t)s2 * T.n_pad;
     const uint16_t *ea = T.dx_se + (size_t)s1 * T.n_pad, *eb = T.dx_se + (size_t)s2 * T.n_pad;

@@ -26,10 +26,12 @@ struct PairChunk {
   uint64_t n_pairs;
 };
 
-// Counters a scan accumulates on the device.
+// Counters a scan accumulates on the device.  The first NGSLD_WORK_COUNTERS fields are reset per chunk.
+#define NGSLD_WORK_COUNTERS 3
 struct DevCounters {
-  unsigned long long next_pair;   // dynamic work counter (list kernels)
-  unsigned long long next_tile;   // dynamic work counter (tile kernel)
+  unsigned long long next_pair;     // dynamic work counter (list / warp EM kernels)
+  unsigned long long next_tile;     // dynamic work counter (tile kernel)
+  unsigned long long next_pearson;  // dynamic work counter (r2_ExpG kernel)
   unsigned long long em_passes;   // total EM passes executed
 };
 

@@ -422,7 +422,7 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch) {
   if (path && strcmp(path, "warp") != 0) return NGSLD_OK;
   const uint64_t min_ind = path ? 1 : 160;  // below: the sub-warp group kernels waste fewer lanes
   if (c->n_ind < min_ind) return NGSLD_OK;
-  int r = (int)std::min<uint64_t>(8, (c->n_ind + 31) / 32);
+  int r = (int)std::min<uint64_t>(6, (c->n_ind + 31) / 32);
   const char *force = getenv("NGSLD_WARP_R");
   if (force && atoi(force) >= 1 && atoi(force) <= 8) r = atoi(force);
   const emwarp::WarpVariant *w = &emwarp::warp_variants[r - 1];
@@ -430,7 +430,7 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch) {
   const size_t smem = emwarp::WARPS_PER_CTA * 2 * tail_pad * 24;
   if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
   int occ = 0;
-  for (const void *fn : {w->fn, w->fn_ign}) {
+  for (const void *fn : {w->fn, w->fn_ign, w->fn_u1}) {
     CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, emwarp::CTA_THREADS, smem));
   }
@@ -448,7 +448,9 @@ int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
   void *args[] = {&Tt, &Cc, &ctr};
   const unsigned long long want = (C.n_pairs + emwarp::WARPS_PER_CTA - 1) / emwarp::WARPS_PER_CTA;
   const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_warp);
-  CUDA_TRY(c, cudaLaunchKernel(ignore_miss ? ch.w->fn_ign : ch.w->fn, dim3(blocks), dim3(emwarp::CTA_THREADS), args,
+  const char *u1 = getenv("NGSLD_WARP_U1");  // experiments: unfused tail loop
+  const void *fn = ignore_miss ? ch.w->fn_ign : (u1 && atoi(u1) ? ch.w->fn_u1 : ch.w->fn);
+  CUDA_TRY(c, cudaLaunchKernel(fn, dim3(blocks), dim3(emwarp::CTA_THREADS), args,
                                ch.warp_smem, c->s_main));
   return NGSLD_OK;
 }
@@ -522,18 +524,20 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   }
   aux::fill_rows_kernel<<<gblocks, threads, 0, c->s_main>>>(T, C);
   c->stats.n_launches += 2;
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, NGSLD_WORK_COUNTERS * sizeof(unsigned long long), c->s_main));
   CUDA_TRY(c, cudaEventRecord(b.ev_ready, c->s_main));
-  // r2_ExpG on the auxiliary stream, concurrently with the EM
+  // r2_ExpG on the auxiliary stream, launched BEFORE the EM so that its CTAs are resident beside the EM's
   CUDA_TRY(c, cudaStreamWaitEvent(c->s_aux, b.ev_ready, 0));
   CUDA_TRY(c, cudaEventRecord(b.ev_p0, c->s_aux));
   {
-    const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
-    aux::pearson_kernel<<<pb, 128, 0, c->s_aux>>>(T, C);
+    const bool beside_em = ch.w != nullptr && !P.strict;
+    const unsigned long long want = (n + 127) / 128;
+    const unsigned pb = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * (beside_em ? 1 : 16));
+    aux::pearson_kernel<<<pb, 128, 0, c->s_aux>>>(T, C, c->d_ctr);
     c->stats.n_launches++;
   }
   CUDA_TRY(c, cudaEventRecord(b.ev_p1, c->s_aux));
   // EM
-  CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
   CUDA_TRY(c, cudaEventRecord(b.ev_em0, c->s_main));
   if (P.strict || (ch.v == nullptr && ch.w == nullptr)) {
     const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
@@ -1214,8 +1218,8 @@ int ngsld_pairs(ngsld_ctx *c, const uint32_t *s1, const uint32_t *s2, uint64_t n
     const unsigned gb = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 32);
     aux::fill_rows_kernel<<<gb, 256, 0, c->s_main>>>(T, C);
     const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
-    aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C);
-    CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(unsigned long long), c->s_main));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, NGSLD_WORK_COUNTERS * sizeof(unsigned long long), c->s_main));
+    aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C, c->d_ctr);
     if (strict || (!ch.v && !ch.w)) {
       aux::em_strict_kernel<<<pb, 128, 0, c->s_main>>>(T, C, ignore_miss_data, c->d_ctr);
     } else if (ch.w) {

@@ -46,6 +46,46 @@ __device__ __forceinline__ void estep(const double f0, const double f1, const do
   s = __fma_rn(f3, i3, __fma_rn(f2, i2, __fma_rn(f1, i1, f0 * i0)));
 }
 
+__device__ __forceinline__ void accum(double &a0, double &a1, double &a2, double &a3, double i0, double i1, double i2,
+                                      double i3, double inv) {
+  a0 = __fma_rn(i0, inv, a0);
+  a1 = __fma_rn(i1, inv, a1);
+  a2 = __fma_rn(i2, inv, a2);
+  a3 = __fma_rn(i3, inv, a3);
+}
+
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// A lane's two adjacent individuals of one tail iteration: 48 contiguous bytes of each row slice.
+struct TailVec {
+  double2 a0, a1, a2, b0, b1, b2;
+  __device__ __forceinline__ void load(uint32_t sa, uint32_t sb) {
+    a0 = lds128(sa); a1 = lds128(sa + 16); a2 = lds128(sa + 32);
+    b0 = lds128(sb); b1 = lds128(sb + 16); b2 = lds128(sb + 32);
+  }
+  template <bool MASKED>
+  __device__ __forceinline__ void run(double f0, double f1, double f2, double f3, double &s0, double &s1, double &s2,
+                                      double &s3, bool ok_a, bool ok_b) const {
+    Ind ga, gb;
+    ga.p0 = a0.x; ga.p1 = a0.y; ga.p2 = a1.x; gb.p0 = a1.y; gb.p1 = a2.x; gb.p2 = a2.y;
+    ga.q0 = b0.x; ga.q1 = b0.y; ga.q2 = b1.x; gb.q0 = b1.y; gb.q1 = b2.x; gb.q2 = b2.y;
+    double i0, i1, i2, i3, s, k0, k1, k2, k3, t;
+    estep(f0, f1, f2, f3, ga, i0, i1, i2, i3, s);
+    estep(f0, f1, f2, f3, gb, k0, k1, k2, k3, t);
+    double inv_a = emfast::rcp_fast(s), inv_b = emfast::rcp_fast(t);
+    if (MASKED) {
+      if (!ok_a) inv_a = 0.0;
+      if (!ok_b) inv_b = 0.0;
+    }
+    accum(s0, s1, s2, s3, i0, i1, i2, i3, inv_a);
+    accum(s0, s1, s2, s3, k0, k1, k2, k3, inv_b);
+  }
+};
+
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 __device__ __forceinline__ double shfl_idx_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 
@@ -71,8 +111,11 @@ __device__ __forceinline__ void warp_sum4(double &a0, double &a1, double &a2, do
 // R    individuals per lane held in registers (individuals lane + 32 r, r < R)
 // IGN  --ignore_miss_data: individuals whose likelihoods are flat at either site are left out
 // Dynamic shared memory: WARPS_PER_CTA * 2 * tail_bytes, tail_bytes = (n_pad - 32 R) * 24 (0 if n_pad <= 32 R).
-template <int R, bool IGN>
-__global__ void __launch_bounds__(CTA_THREADS, (R <= 4 ? 4 : 3)) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
+// U    full tail iterations fused per loop trip (2U individuals in flight per lane)
+// Register cap: 144 (R >= 5) keeps three CTAs (55 K registers) plus one CTA of the r2_ExpG kernel resident per SM;
+// 128 (R <= 4) allows four CTAs.
+template <int R, bool IGN, int U>
+__global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t bars[WARPS_PER_CTA];
 
@@ -91,6 +134,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (R <= 4 ? 4 : 3)) em_warp_kernel(
   uint32_t phase = 0;
   unsigned long long my_passes = 0;
   const uint32_t n_iter_tail = (tail_n + 63u) / 64u;  // each lane handles individuals 2*lane + 64*j (+1)
+  const uint32_t n_full = tail_n / 64u;               // iterations in which every lane has two valid individuals
+  const uint32_t sa = emfast::smem_u32(dyn_smem) + (uint32_t)warp * 2u * tail_bytes + (uint32_t)lane * 48u;
+  const uint32_t sb = sa + tail_bytes;
 
   for (;;) {
     unsigned long long idx = 0;
@@ -163,48 +209,46 @@ __global__ void __launch_bounds__(CTA_THREADS, (R <= 4 ? 4 : 3)) em_warp_kernel(
     for (;;) {
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       // ---- register-resident individuals ----
+      if (IGN || !reg_full) {
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        double i0, i1, i2, i3, s;
-        estep(f0, f1, f2, f3, g[r], i0, i1, i2, i3, s);
-        double inv = emfast::rcp_fast(s);
-        if (IGN || !reg_full)
+        for (int r = 0; r < R; r++) {
+          double i0, i1, i2, i3, s;
+          estep(f0, f1, f2, f3, g[r], i0, i1, i2, i3, s);
+          double inv = emfast::rcp_fast(s);
           if (!((rmask >> r) & 1u)) inv = 0.0;
-        a0 = __fma_rn(i0, inv, a0);
-        a1 = __fma_rn(i1, inv, a1);
-        a2 = __fma_rn(i2, inv, a2);
-        a3 = __fma_rn(i3, inv, a3);
+          accum(a0, a1, a2, a3, i0, i1, i2, i3, inv);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          double i0, i1, i2, i3, s;
+          estep(f0, f1, f2, f3, g[r], i0, i1, i2, i3, s);
+          accum(a0, a1, a2, a3, i0, i1, i2, i3, emfast::rcp_fast(s));
+        }
       }
       // ---- individuals streamed from the warp's shared-memory slice ----
-#pragma unroll 2
-      for (uint32_t j = 0; j < n_iter_tail; j++) {
+      uint32_t j = 0;
+      if (!IGN) {
+        // iterations in which all 32 lanes own two valid individuals: no masks, U iterations fused for ILP
+        for (; j + U <= n_full; j += U) {
+          TailVec v[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) v[u].load(sa + (j + u) * 1536u, sb + (j + u) * 1536u);
+#pragma unroll
+          for (int u = 0; u < U; u++) v[u].template run<false>(f0, f1, f2, f3, a0, a1, a2, a3, true, true);
+        }
+      }
+      for (; j < n_iter_tail; j++) {
         const uint32_t i0x = 2u * lane + 64u * j;
         if (i0x < tail_n) {
-          const double2 *pa = reinterpret_cast<const double2 *>(tail_a + 3 * (size_t)i0x);
-          const double2 *pb = reinterpret_cast<const double2 *>(tail_b + 3 * (size_t)i0x);
-          const double2 pa0 = pa[0], pa1 = pa[1], pa2 = pa[2];
-          const double2 pb0 = pb[0], pb1 = pb[1], pb2 = pb[2];
-          Ind ga, gb;
-          ga.p0 = pa0.x; ga.p1 = pa0.y; ga.p2 = pa1.x; gb.p0 = pa1.y; gb.p1 = pa2.x; gb.p2 = pa2.y;
-          ga.q0 = pb0.x; ga.q1 = pb0.y; ga.q2 = pb1.x; gb.q0 = pb1.y; gb.q1 = pb2.x; gb.q2 = pb2.y;
-          double i0, i1, i2, i3, s, k0, k1, k2, k3, t;
-          estep(f0, f1, f2, f3, ga, i0, i1, i2, i3, s);
-          estep(f0, f1, f2, f3, gb, k0, k1, k2, k3, t);
-          double inv_a = emfast::rcp_fast(s), inv_b = emfast::rcp_fast(t);
+          TailVec v;
+          v.load(sa + j * 1536u, sb + j * 1536u);
+          bool ok_a = true, ok_b = i0x + 1 < tail_n;  // odd sample size: the pad slot is left out
           if (IGN) {
-            if (!((tmask >> (2 * j)) & 1ull)) inv_a = 0.0;
-            if (!((tmask >> (2 * j + 1)) & 1ull)) inv_b = 0.0;
-          } else if (i0x + 1 >= tail_n) {
-            inv_b = 0.0;  // odd sample size: the pad slot
+            ok_a = (tmask >> (2 * j)) & 1ull;
+            ok_b = (tmask >> (2 * j + 1)) & 1ull;
           }
-          a0 = __fma_rn(i0, inv_a, a0);
-          a1 = __fma_rn(i1, inv_a, a1);
-          a2 = __fma_rn(i2, inv_a, a2);
-          a3 = __fma_rn(i3, inv_a, a3);
-          a0 = __fma_rn(k0, inv_b, a0);
-          a1 = __fma_rn(k1, inv_b, a1);
-          a2 = __fma_rn(k2, inv_b, a2);
-          a3 = __fma_rn(k3, inv_b, a3);
+          v.template run<true>(f0, f1, f2, f3, a0, a1, a2, a3, ok_a, ok_b);
         }
       }
       warp_sum4(a0, a1, a2, a3, lane);
@@ -238,7 +282,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (R <= 4 ? 4 : 3)) em_warp_kernel(
 
 struct WarpVariant {
   int r;
-  const void *fn, *fn_ign;
+  const void *fn, *fn_ign, *fn_u1;  // default (2 tail iterations fused), --ignore_miss_data, unfused
 };
 
 }  // namespace emwarp
