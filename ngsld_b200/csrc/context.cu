@@ -422,19 +422,35 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch) {
   if (path && strcmp(path, "warp") != 0) return NGSLD_OK;
   const uint64_t min_ind = path ? 1 : 160;  // below: the sub-warp group kernels waste fewer lanes
   if (c->n_ind < min_ind) return NGSLD_OK;
-  int r = (int)std::min<uint64_t>(6, (c->n_ind + 31) / 32);
-  const char *force = getenv("NGSLD_WARP_R");
-  if (force && atoi(force) >= 1 && atoi(force) <= 8) r = atoi(force);
-  const emwarp::WarpVariant *w = &emwarp::warp_variants[r - 1];
-  const size_t tail_pad = c->n_pad > 32u * (size_t)r ? c->n_pad - 32u * (size_t)r : 0;
-  const size_t smem = emwarp::WARPS_PER_CTA * 2 * tail_pad * 24;
-  if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
+  // smallest group of warps per pair whose per-CTA shared memory lets three CTAs share an SM
+  const char *force = getenv("NGSLD_WARP_R"), *force_g = getenv("NGSLD_WARP_G");
+  const emwarp::WarpVariant *w = nullptr;
+  size_t smem = 0;
   int occ = 0;
-  for (const void *fn : {w->fn, w->fn_ign, w->fn_u1}) {
-    CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, emwarp::CTA_THREADS, smem));
+  for (int g : {1, 2, 4}) {
+    if (force_g && atoi(force_g) != g) continue;
+    const uint64_t per_warp = (c->n_ind + g - 1) / g;
+    int r = (int)std::min<uint64_t>(6, (per_warp + 31) / 32);
+    if (force && atoi(force) >= 1 && atoi(force) <= 8) r = atoi(force);
+    const emwarp::WarpVariant *cand = nullptr;
+    for (int k = 0; k < emwarp::warp_variants_count; k++)
+      if (emwarp::warp_variants[k].r == r && emwarp::warp_variants[k].g == g) cand = &emwarp::warp_variants[k];
+    if (!cand) continue;
+    const size_t sm = (size_t)emwarp::WARPS_PER_CTA * 2 * emwarp::WarpGeom::tail_slots((uint32_t)c->n_pad, g, r) * 24;
+    if (sm + 2048 > (size_t)c->smem_optin) continue;
+    int o = 0;
+    for (const void *fn : {cand->fn, cand->fn_ign, cand->fn_u1}) {
+      CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, emwarp::CTA_THREADS, sm));
+    }
+    if (o > occ) {
+      w = cand;
+      smem = sm;
+      occ = o;
+    }
+    if (occ >= 3) break;
   }
-  if (occ < 3 && !path) return NGSLD_OK;
+  if (!w || (occ < 3 && !path)) return NGSLD_OK;
   ch.w = w;
   ch.warp_smem = smem;
   ch.blocks_warp = std::max(1, occ) * c->sm_count;

@@ -32,6 +32,20 @@ struct Ind {
   double p0, p1, p2, q0, q1, q2;
 };
 
+// How a row of n_pad individual slots is divided among the G warps of a pair (host and device agree on this).
+struct WarpGeom {
+  // slots per warp: even (16-byte aligned slices) and a multiple of 2
+  __host__ __device__ static inline uint32_t slice(uint32_t n_pad, int g) {
+    const uint32_t s = (n_pad + (uint32_t)g - 1u) / (uint32_t)g;
+    return (s + 1u) & ~1u;
+  }
+  // shared-memory slots per warp and row: the largest tail among the group's warps (the first warp's)
+  __host__ __device__ static inline uint32_t tail_slots(uint32_t n_pad, int g, int r) {
+    const uint32_t s = slice(n_pad, g) < n_pad ? slice(n_pad, g) : n_pad;
+    return s > 32u * (uint32_t)r ? s - 32u * (uint32_t)r : 0u;
+  }
+};
+
 // one individual's E-step contribution
 __device__ __forceinline__ void estep(const double f0, const double f1, const double f2, const double f3, const Ind &g,
                                       double &i0, double &i1, double &i2, double &i3, double &s) {
@@ -112,22 +126,34 @@ __device__ __forceinline__ void warp_sum4(double &a0, double &a1, double &a2, do
 // IGN  --ignore_miss_data: individuals whose likelihoods are flat at either site are left out
 // Dynamic shared memory: WARPS_PER_CTA * 2 * tail_bytes, tail_bytes = (n_pad - 32 R) * 24 (0 if n_pad <= 32 R).
 // U    full tail iterations fused per loop trip (2U individuals in flight per lane)
+// G    warps per pair (1, 2 or 4): warp w of a group owns the individuals [w*slice, (w+1)*slice) of both rows
+//      (slice = WarpGeom::slice(n_pad, G)); the G partial sums of a pass meet in shared memory behind a named
+//      barrier, and every warp of the group then performs the identical M-step.  G > 1 keeps the per-warp
+//      footprint of a 500-individual pair for samples of 1000 (G = 2) or 2000 (G = 4) individuals.
 // Register cap: 144 (R >= 5) keeps three CTAs (55 K registers) plus one CTA of the r2_ExpG kernel resident per SM;
 // 128 (R <= 4) allows four CTAs.
-template <int R, bool IGN, int U>
+template <int R, bool IGN, int U, int G>
 __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t bars[WARPS_PER_CTA];
+  __shared__ double red[WARPS_PER_CTA / G][2][G][4];            // per group, double-buffered by pass parity
+  __shared__ unsigned long long fetched[WARPS_PER_CTA / G];     // pair index handed to the group's warps
+  __shared__ unsigned int used_cnt[WARPS_PER_CTA / G][G];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_ind = T.n_ind;
+  const int grp = warp / G, gw = warp % G;                      // group in the CTA, warp in the group
+  const uint32_t slice = WarpGeom::slice(T.n_pad, G);
+  const uint32_t lo = (uint32_t)gw * slice;                     // first individual of this warp's slice
+  const uint32_t n_ind = T.n_ind > lo ? (T.n_ind - lo < slice ? T.n_ind - lo : slice) : 0u;   // individuals in the slice
+  const uint32_t n_padw = T.n_pad > lo ? (T.n_pad - lo < slice ? T.n_pad - lo : slice) : 0u;  // row slots in the slice
   const uint32_t reg_n = n_ind < 32u * R ? n_ind : 32u * R;       // individuals covered by registers
   const uint32_t tail_n = n_ind - reg_n;                          // individuals streamed from shared memory
-  const uint32_t tail_pad = T.n_pad > 32u * R ? T.n_pad - 32u * R : 0u;
-  const uint32_t tail_bytes = tail_pad * 24u;
+  const uint32_t tail_pad = n_padw > 32u * R ? n_padw - 32u * R : 0u;
+  const uint32_t tail_bytes = tail_pad * 24u;                     // this warp's copy size
+  const uint32_t slot_bytes = WarpGeom::tail_slots(T.n_pad, G, R) * 24u;  // every warp's slot size (the largest tail)
   const size_t row_doubles = (size_t)T.n_pad * 3;
-  const double *tail_a = reinterpret_cast<const double *>(dyn_smem + (size_t)warp * 2 * tail_bytes);
-  const double *tail_b = tail_a + (size_t)tail_pad * 3;
+  const double *tail_a = reinterpret_cast<const double *>(dyn_smem + (size_t)warp * 2 * slot_bytes);
+  const double *tail_b = reinterpret_cast<const double *>(dyn_smem + (size_t)warp * 2 * slot_bytes + slot_bytes);
   uint64_t *bar = &bars[warp];
   if (lane == 0) emfast::mbar_init(bar, 1);
   __syncwarp();
@@ -135,16 +161,23 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
   unsigned long long my_passes = 0;
   const uint32_t n_iter_tail = (tail_n + 63u) / 64u;  // each lane handles individuals 2*lane + 64*j (+1)
   const uint32_t n_full = tail_n / 64u;               // iterations in which every lane has two valid individuals
-  const uint32_t sa = emfast::smem_u32(dyn_smem) + (uint32_t)warp * 2u * tail_bytes + (uint32_t)lane * 48u;
-  const uint32_t sb = sa + tail_bytes;
+  const uint32_t sa = emfast::smem_u32(dyn_smem) + (uint32_t)warp * 2u * slot_bytes + (uint32_t)lane * 48u;
+  const uint32_t sb = sa + slot_bytes;
 
   for (;;) {
     unsigned long long idx = 0;
-    if (lane == 0) idx = atomicAdd(&ctr->next_pair, 1ull);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (G == 1) {
+      if (lane == 0) idx = atomicAdd(&ctr->next_pair, 1ull);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+    } else {
+      // the last reduction barrier of the previous pair orders every read of fetched[] before this write
+      if (gw == 0 && lane == 0) fetched[grp] = atomicAdd(&ctr->next_pair, 1ull);
+      emfast::named_bar_sync(1 + grp, 32 * G);
+      idx = fetched[grp];
+    }
     if (idx >= C.n_pairs) break;
     const uint32_t s1 = C.s1[idx], s2 = C.s2[idx];
-    const double *row_a = T.gl + (size_t)s1 * row_doubles, *row_b = T.gl + (size_t)s2 * row_doubles;
+    const double *row_a = T.gl + ((size_t)s1 * T.n_pad + lo) * 3, *row_b = T.gl + ((size_t)s2 * T.n_pad + lo) * 3;
 
     // ---- stage the row tails (async proxy) while the register part is loaded ----
     if (tail_bytes) {
@@ -177,7 +210,7 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
     }
     // tail mask (only with IGN): bit 2j / 2j+1 = the lane's two individuals of tail iteration j take part
     unsigned long long tmask = ~0ull;
-    uint32_t n_used = n_ind;
+    uint32_t n_used = T.n_ind;
     if (IGN) {
       tmask = 0;
       for (uint32_t j = 0; j < n_iter_tail; j++) {
@@ -194,6 +227,13 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
       uint32_t cnt = __popc(rmask) + __popcll(tmask);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (G > 1) {
+        if (lane == 0) used_cnt[grp][gw] = cnt;
+        emfast::named_bar_sync(1 + grp, 32 * G);
+        cnt = 0;
+#pragma unroll
+        for (int w = 0; w < G; w++) cnt += used_cnt[grp][w];
+      }
       n_used = cnt;
     }
     const double inv_x = __ddiv_rn(1.0, (double)n_used);
@@ -252,6 +292,20 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
         }
       }
       warp_sum4(a0, a1, a2, a3, lane);
+      if (G > 1) {
+        const int par = it & 1;
+        if (lane == 0) {
+          double *slot = red[grp][par][gw];
+          slot[0] = a0; slot[1] = a1; slot[2] = a2; slot[3] = a3;
+        }
+        emfast::named_bar_sync(1 + grp, 32 * G);
+        a0 = a1 = a2 = a3 = 0.0;
+#pragma unroll
+        for (int w = 0; w < G; w++) {  // same order in every warp of the group: identical bits everywhere
+          const double *slot = red[grp][par][w];
+          a0 += slot[0]; a1 += slot[1]; a2 += slot[2]; a3 += slot[3];
+        }
+      }
       // ---- M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5) ----
       A0 = f0 * a0; A1 = f1 * a1; A2 = f2 * a2; A3 = f3 * a3;
       const double n0 = A0 * inv_x, n1 = A1 * inv_x, n2 = A2 * inv_x, n3 = A3 * inv_x;
@@ -265,7 +319,7 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
       if (conv || it == NGSLD_ITER_MAX - 1) break;
       it++;
     }
-    if (lane == 0) {
+    if (lane == 0 && gw == 0) {
       // Output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113): true divisions and the
       // sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes.
       const double xd = (double)n_used;
@@ -281,7 +335,7 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
 }
 
 struct WarpVariant {
-  int r;
+  int r, g;
   const void *fn, *fn_ign, *fn_u1;  // default (2 tail iterations fused), --ignore_miss_data, unfused
 };
 
