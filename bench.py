@@ -226,6 +226,13 @@ def main():
 
     GL, pos = make_inputs(a)
     gl, expg, maf = N.prepare_sites(GL)
+
+    def pinned(x):  # host buffers of the end-to-end leg live in pinned memory (driver contract)
+        t = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = x
+        return t
+    pin_keep = [pinned(gl), pinned(expg), pinned(maf)]
+    gl, expg, maf = (t.numpy() for t in pin_keep)
     pos_dist = np.diff(np.concatenate([[0], pos])).astype(np.float64)
     eng = N.Engine(local)
     stream = torch.cuda.Stream()
@@ -266,8 +273,10 @@ def main():
     ev0.record(stream)
     pairs = launches = passes = 0
     ms_em = ms_pearson = 0.0
+    em_kernel = ""
     for k in range(a.warmup, n_steps):
         st = eng.scan_device(P, *slab(k)[:2])
+        em_kernel = st["em_kernel"]
         pairs += st["n_pairs"]
         launches += st["n_launches"]
         passes += st["sum_em_passes"]
@@ -332,18 +341,25 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         if hbm_peak <= 0:
             hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # FP64 work actually bounding the kernel: 27 FP64 instr + 1 reciprocal (~33 issue slots, 40 flop)
-        # per (individual, EM pass)  [SURVEY.md §8(d)]
-        flop = passes * a.n_ind * 40.0
+        # FP64 work that actually bounds the kernel, per (individual, EM pass): 9 DMUL + 18 DFMA (+ 1 MUFU seed)
+        # = 27 FP64 instructions = 45 flop [em_warp.cuh header; SURVEY.md §8(d) rounds this to 40]
+        n_chunks = max(1, launches // 4)  # expand, fill, r2_ExpG, EM per chunk
+        flop = passes * a.n_ind * 45.0
         fp64_achieved = flop / em_s / 1e9
+        issue = passes * a.n_ind * 27.0 / em_s / (fp64_peak * 1e9 / 2.0) if fp64_peak else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "emfast::em_tile_kernel",
-                    "algorithmic_bytes_per_pair": bpp, "launch_ms_avg": ms_em / max(1, a.steps),
-                    "note": "path is FP64-issue-bound (~%.0f EM passes/pair); see fp64" % (passes / max(1, pairs)),
+                    "traffic": None, "peak_source": peak_src, "kernel": em_kernel,
+                    "algorithmic_bytes_per_pair": bpp, "launch_ms_avg": ms_em / n_chunks,
+                    "launches_timed": n_chunks,
+                    "note": "path is FP64-issue-bound (~%.0f EM passes/pair), not HBM-bound; see fp64" % (passes / max(1, pairs)),
                     "fp64": {"achieved_gflops": fp64_achieved, "peak_gflops": fp64_peak,
                              "frac": fp64_achieved / fp64_peak if fp64_peak else None,
-                             "peak_source": "ngsld_probe_fp64 (DFMA issue micro-benchmark, this GPU, this run)",
-                             "flop_per_ind_pass": 40, "mean_em_passes_per_pair": passes / max(1, pairs)}}
+                             "issue_frac": issue,
+                             "peak_source": "ngsld_probe_fp64 (DFMA issue micro-benchmark with 2 register operands, this GPU, "
+                                            "this run); DFMAs reading 3 distinct registers issue at 0.73 of it "
+                                            "(scripts/micro/fp64_ops.cu)",
+                             "flop_per_ind_pass": 45, "fp64_instr_per_ind_pass": 27,
+                             "mean_em_passes_per_pair": passes / max(1, pairs)}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

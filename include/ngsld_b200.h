@@ -82,6 +82,7 @@ typedef struct {
   double ms_device_total;  /* first launch -> last result byte in host memory          */
   double ms_plan;          /* host planning (windows, sampling)                       */
   uint64_t h2d_bytes, d2h_bytes;
+  char em_kernel[64];      /* EM kernel family the scan used, e.g. "emwarp::em_warp_kernel<R=6,G=1>" */
 } ngsld_scan_stats;
 
 /* sinks: called on the scanning host thread, rows in (s1, s2) order — the order the reference

@@ -554,6 +554,13 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   }
   CUDA_TRY(c, cudaEventRecord(b.ev_p1, c->s_aux));
   // EM
+  if (P.strict || (ch.v == nullptr && ch.w == nullptr))
+    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "aux::em_strict_kernel");
+  else if (ch.w)
+    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emwarp::em_warp_kernel<R=%d,G=%d>", ch.w->r, ch.w->g);
+  else
+    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emfast::em_%s_kernel<IPL=%d,LPG=%d>", ch.tile ? "tile" : "list",
+             ch.v->ipl, ch.v->lpg);
   CUDA_TRY(c, cudaEventRecord(b.ev_em0, c->s_main));
   if (P.strict || (ch.v == nullptr && ch.w == nullptr)) {
     const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
