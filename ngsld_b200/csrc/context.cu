@@ -477,24 +477,27 @@ int choose_em(ngsld_ctx *c, const Plan &pl, EmChoice &ch) {
   ch.v = pick_variant(c->n_ind);
   if (!ch.v) return NGSLD_OK;  // falls back to the strict kernel (n_ind > 2048)
   int occ = 0;
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->list_fn, emfast::CTA_THREADS, 0));
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->list_fn, std::max(emfast::CTA_THREADS, ch.v->lpg), 0));
   ch.blocks_list = std::max(1, occ) * c->sm_count;
+  // Site-tile staging (TMA) is optional for the group kernels: the rows of a pair are read once per pair and L2
+  // serves them at a small fraction of its bandwidth, so the default is the plain pair list, which leaves the shared
+  // memory free and lets 3-4 CTAs share an SM.  NGSLD_EM_PATH=tile turns the tiles on (a third of the SM's shared
+  // memory per CTA).
   const size_t row_bytes = c->n_pad * 24;
-  const size_t budget = (size_t)c->smem_optin - 4096;
+  const size_t budget = ((size_t)c->smem_optin - 4096) / 3;
   uint32_t rows_fit = (uint32_t)std::min<size_t>(budget / row_bytes, 64);
   uint32_t t = rows_fit / 2;
   if (t > 32) t = 32;
   const char *path = getenv("NGSLD_EM_PATH");  // "list" | "tile" for experiments
   const char *tdim = getenv("NGSLD_TILE");
   if (tdim && atoi(tdim) > 0 && (uint32_t)atoi(tdim) <= t) t = atoi(tdim);
-  ch.tile = !pl.sampled && t >= 4;
-  if (path && !strcmp(path, "list")) ch.tile = false;
+  ch.tile = false;
   if (path && !strcmp(path, "tile") && !pl.sampled && t >= 1) ch.tile = true;
   if (ch.tile) {
     ch.TA = ch.TB = t;
     ch.dyn_smem = (size_t)(ch.TA + ch.TB) * row_bytes;
     CUDA_TRY(c, cudaFuncSetAttribute(ch.v->tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.dyn_smem));
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->tile_fn, emfast::CTA_THREADS, ch.dyn_smem));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->tile_fn, std::max(emfast::CTA_THREADS, ch.v->lpg), ch.dyn_smem));
     ch.blocks_tile = std::max(1, occ) * c->sm_count;
   }
   return NGSLD_OK;
@@ -586,16 +589,16 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
     DevCounters *ctr = c->d_ctr;
     void *args[] = {&Tt, &rows, &A, &ign, &ctr};
     const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<size_t>(t1 - t0, 1), ch.blocks_tile);
-    CUDA_TRY(c, cudaLaunchKernel(ch.v->tile_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, ch.dyn_smem, c->s_main));
+    CUDA_TRY(c, cudaLaunchKernel(ch.v->tile_fn, dim3(blocks), dim3(std::max(emfast::CTA_THREADS, ch.v->lpg)), args, ch.dyn_smem, c->s_main));
   } else {
     int ign = P.ignore_miss_data;
     SiteTable Tt = T;
     PairChunk Cc = C;
     DevCounters *ctr = c->d_ctr;
     void *args[] = {&Tt, &Cc, &ign, &ctr};
-    const unsigned long long groups_per_cta = emfast::CTA_THREADS / ch.v->lpg;
+    const unsigned long long groups_per_cta = std::max(emfast::CTA_THREADS, ch.v->lpg) / ch.v->lpg;
     const unsigned blocks = (unsigned)std::min<unsigned long long>((n + groups_per_cta - 1) / groups_per_cta, ch.blocks_list);
-    CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, 0, c->s_main));
+    CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(std::max(emfast::CTA_THREADS, ch.v->lpg)), args, 0, c->s_main));
   }
   c->stats.n_launches++;
   CUDA_TRY(c, cudaEventRecord(b.ev_em1, c->s_main));
@@ -1254,9 +1257,9 @@ int ngsld_pairs(ngsld_ctx *c, const uint32_t *s1, const uint32_t *s2, uint64_t n
       PairChunk Cc = C;
       DevCounters *ctr = c->d_ctr;
       void *args[] = {&Tt, &Cc, &ign, &ctr};
-      const unsigned long long gpc = emfast::CTA_THREADS / ch.v->lpg;
+      const unsigned long long gpc = std::max(emfast::CTA_THREADS, ch.v->lpg) / ch.v->lpg;
       const unsigned blocks = (unsigned)std::min<unsigned long long>((n + gpc - 1) / gpc, ch.blocks_list);
-      CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(emfast::CTA_THREADS), args, 0, c->s_main));
+      CUDA_TRY(c, cudaLaunchKernel(ch.v->list_fn, dim3(blocks), dim3(std::max(emfast::CTA_THREADS, ch.v->lpg)), args, 0, c->s_main));
     }
     c->stats.n_launches += 3;
     CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, n * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_main));

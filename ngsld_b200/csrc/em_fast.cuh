@@ -2,14 +2,12 @@
 // shared/gen_func.cpp:1027-1119) for sm_100a.
 //
 // Work decomposition: one GROUP of LPG lanes owns one site pair; each lane keeps IPL individuals of
-// that pair ENTIRELY IN REGISTERS for the whole EM as the nine products L[a][b] = p1[a]*p2[b]
-// (iteration-invariant), so the <=100 EM passes touch no memory at all.  LPG < 32: several groups
-// share a warp; LPG > 32: a group spans LPG/32 warps and combines through shared memory + a named
-// barrier.  Per pass and individual the E-step is
-//     t_k = sum_h (f_k f_h) L[G1(k,h)][G2(k,h)]        (16 FP64: 4 mul + 12 fma)
-//     s   = (t0+t1)+(t2+t3)                            ( 3 add)  == the reference's `sum`
-//     acc_k += t_k / s                                 ( 1 MUFU + 3 fma reciprocal, 4 fma)
-// and the M-step is f_k = acc_k / n_used (the reference's tmp_k equals 2 t_k and its f = ff/(2x)).
+// that pair ENTIRELY IN REGISTERS for the whole EM (their six genotype likelihoods), so the <=100 EM
+// passes touch no memory at all.  LPG < 32: several groups share a warp; LPG > 32: a group spans
+// LPG/32 warps and combines through shared memory + a named barrier.  Per pass and individual the
+// E-step is estep() below (27 FP64 + 1 MUFU; same arithmetic as the warp-per-pair kernel of
+// em_warp.cuh), and the M-step is f_k <- f_k A_k / n_used with A_k the group-wide sum of i_k / s
+// (f_k i_k is the reference's tmp_k / 2 and its M-step is ff/(2x)).
 // The reference's sequential renormalisation divides by 1 +- 1ulp; it is skipped inside the pass loop and
 // applied once to the frequencies that are written out.  Results agree with the bit-faithful kernel
 // (aux_kernels.cu) to ~1e-15, far inside the 1e-9 contract, at equal nIter.
@@ -22,7 +20,31 @@
 
 namespace emfast {
 
-constexpr int CTA_THREADS = 256;
+constexpr int CTA_THREADS = 128;                         // four warps; groups wider than that get their own CTA size
+template <int LPG>
+struct Cta {
+  static constexpr int THREADS = LPG > CTA_THREADS ? LPG : CTA_THREADS;
+};
+
+struct Ind {
+  double p0, p1, p2, q0, q1, q2;
+};
+
+// One individual's E-step:  u0 = f0 q0 + f1 q1   u1 = f2 q0 + f3 q1   v0 = f0 q1 + f1 q2   v1 = f2 q1 + f3 q2
+//                           i0 = p0 u0 + p1 u1   i1 = p0 v0 + p1 v1   i2 = p1 u0 + p2 u1   i3 = p1 v0 + p2 v1
+//                           s  = f0 i0 + f1 i1 + f2 i2 + f3 i3   (== the reference's `sum`, gen_func.cpp:1094-1096)
+__device__ __forceinline__ void estep(const double f0, const double f1, const double f2, const double f3, const Ind &g,
+                                      double &i0, double &i1, double &i2, double &i3, double &s) {
+  const double u0 = __fma_rn(f1, g.q1, f0 * g.q0);
+  const double u1 = __fma_rn(f3, g.q1, f2 * g.q0);
+  const double v0 = __fma_rn(f1, g.q2, f0 * g.q1);
+  const double v1 = __fma_rn(f3, g.q2, f2 * g.q1);
+  i0 = __fma_rn(g.p1, u1, g.p0 * u0);
+  i1 = __fma_rn(g.p1, v1, g.p0 * v0);
+  i2 = __fma_rn(g.p2, u1, g.p1 * u0);
+  i3 = __fma_rn(g.p2, v1, g.p1 * v0);
+  s = __fma_rn(f3, i3, __fma_rn(f2, i2, __fma_rn(f1, i1, f0 * i0)));
+}
 
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
@@ -40,7 +62,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int LPG>
 struct GroupScratch {
   static constexpr int W = LPG > 32 ? LPG / 32 : 1;
-  static constexpr int G = CTA_THREADS / LPG;
+  static constexpr int G = Cta<LPG>::THREADS / LPG;
   double red[G][2][W][4];          // per group, double-buffered by pass parity
   unsigned long long fetched[G][2];  // {output index, row locators} handed to a multi-warp group
   unsigned int n_used[G][W];
@@ -67,7 +89,7 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
   const unsigned gmask = (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~(GL - 1)));
   const int leader = lane & ~(GL - 1);
 
-  double L[IPL][9];
+  Ind gl6[IPL];
   double f[4] = {0, 0, 0, 0};
   double inv_x = 0.0;
   uint32_t vmask = 0, n_used = 0, it = 0, s1 = 0, s2 = 0;
@@ -76,9 +98,7 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
   unsigned long long my_passes = 0;
 
 #pragma unroll
-  for (int j = 0; j < IPL; j++)
-#pragma unroll
-    for (int c = 0; c < 9; c++) L[j][c] = 0.0;
+  for (int j = 0; j < IPL; j++) gl6[j].p0 = gl6[j].p1 = gl6[j].p2 = gl6[j].q0 = gl6[j].q1 = gl6[j].q2 = 0.0;
 
   for (;;) {
     if (need && !done) {
@@ -126,9 +146,8 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
           }
           if (!ok) { p0 = p1 = p2 = 0.0; }
           vmask |= (ok ? 1u : 0u) << j;
-          L[j][0] = p0 * q0; L[j][1] = p0 * q1; L[j][2] = p0 * q2;
-          L[j][3] = p1 * q0; L[j][4] = p1 * q1; L[j][5] = p1 * q2;
-          L[j][6] = p2 * q0; L[j][7] = p2 * q1; L[j][8] = p2 * q2;
+          gl6[j].p0 = p0; gl6[j].p1 = p1; gl6[j].p2 = p2;
+          gl6[j].q0 = q0; gl6[j].q1 = q1; gl6[j].q2 = q2;
         }
         // individuals used by the EM (reference: x in pair_freq_iter)
         uint32_t cnt = __popc(vmask);
@@ -159,24 +178,17 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
     }
 
     // ---------------- one EM pass (uniform across the warp) ----------------
-    const double P00 = f[0] * f[0], P01 = f[0] * f[1], P02 = f[0] * f[2], P03 = f[0] * f[3];
-    const double P11 = f[1] * f[1], P12 = f[1] * f[2], P13 = f[1] * f[3];
-    const double P22 = f[2] * f[2], P23 = f[2] * f[3], P33 = f[3] * f[3];
     double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
 #pragma unroll
     for (int j = 0; j < IPL; j++) {
-      const double *l = L[j];
-      const double t0 = __fma_rn(P03, l[4], __fma_rn(P02, l[3], __fma_rn(P01, l[1], P00 * l[0])));
-      const double t1 = __fma_rn(P13, l[5], __fma_rn(P12, l[4], __fma_rn(P11, l[2], P01 * l[1])));
-      const double t2 = __fma_rn(P23, l[7], __fma_rn(P22, l[6], __fma_rn(P12, l[4], P02 * l[3])));
-      const double t3 = __fma_rn(P33, l[8], __fma_rn(P23, l[7], __fma_rn(P13, l[5], P03 * l[4])));
-      const double s = (t0 + t1) + (t2 + t3);
+      double i0, i1, i2, i3, s;
+      estep(f[0], f[1], f[2], f[3], gl6[j], i0, i1, i2, i3, s);
       double inv = rcp_fast(s);
       if (!((vmask >> j) & 1u)) inv = 0.0;
-      acc0 = __fma_rn(t0, inv, acc0);
-      acc1 = __fma_rn(t1, inv, acc1);
-      acc2 = __fma_rn(t2, inv, acc2);
-      acc3 = __fma_rn(t3, inv, acc3);
+      acc0 = __fma_rn(i0, inv, acc0);
+      acc1 = __fma_rn(i1, inv, acc1);
+      acc2 = __fma_rn(i2, inv, acc2);
+      acc3 = __fma_rn(i3, inv, acc3);
     }
     // group-wide sums (xor butterflies give every lane the same bits)
 #pragma unroll
@@ -201,6 +213,7 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
       }
     }
     // M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5)
+    acc0 *= f[0]; acc1 *= f[1]; acc2 *= f[2]; acc3 *= f[3];
     const double n0 = acc0 * inv_x, n1 = acc1 * inv_x, n2 = acc2 * inv_x, n3 = acc3 * inv_x;
     double eps = 0.0, d;
     d = fabs(n0 - f[0]); if (d > eps) eps = d;

@@ -28,9 +28,8 @@ namespace emwarp {
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 
-struct Ind {
-  double p0, p1, p2, q0, q1, q2;
-};
+using emfast::Ind;
+using emfast::estep;
 
 // How a row of n_pad individual slots is divided among the G warps of a pair (host and device agree on this).
 struct WarpGeom {
@@ -45,20 +44,6 @@ struct WarpGeom {
     return s > 32u * (uint32_t)r ? s - 32u * (uint32_t)r : 0u;
   }
 };
-
-// one individual's E-step contribution
-__device__ __forceinline__ void estep(const double f0, const double f1, const double f2, const double f3, const Ind &g,
-                                      double &i0, double &i1, double &i2, double &i3, double &s) {
-  const double u0 = __fma_rn(f1, g.q1, f0 * g.q0);
-  const double u1 = __fma_rn(f3, g.q1, f2 * g.q0);
-  const double v0 = __fma_rn(f1, g.q2, f0 * g.q1);
-  const double v1 = __fma_rn(f3, g.q2, f2 * g.q1);
-  i0 = __fma_rn(g.p1, u1, g.p0 * u0);
-  i1 = __fma_rn(g.p1, v1, g.p0 * v0);
-  i2 = __fma_rn(g.p2, u1, g.p1 * u0);
-  i3 = __fma_rn(g.p2, v1, g.p1 * v0);
-  s = __fma_rn(f3, i3, __fma_rn(f2, i2, __fma_rn(f1, i1, f0 * i0)));
-}
 
 __device__ __forceinline__ void accum(double &a0, double &a1, double &a2, double &a3, double i0, double i1, double i2,
                                       double i3, double inv) {

@@ -1,0 +1,109 @@
+"""Size-independent properties at bench-like sizes (-m gpu): what can be checked when the oracle would take hours.
+
+  * fast vs strict kernel on a random sample of a large scan (both on the GPU; strict is md5-pinned to the reference)
+  * partition shards concatenate to the whole scan, byte for byte (the multi-GPU sharding unit)
+  * checksum of checksums: the nIter column sums to the kernel's own pass counter
+  * invariants of the domain: haplotype frequencies sum to 1, |D'| <= 1, 0 <= r2 <= 1, swapping the two sites of a
+    pair swaps hap01/hap10 and leaves D, r2, r2_ExpG unchanged
+  * every EM kernel family gives the same answer on the same pairs (warp-per-pair with 1/2/4 warps, group kernels)"""
+import numpy as np
+import pytest
+
+import helpers as H
+import ngsld_b200 as N
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_helpers
+    return gpu_helpers
+
+
+@pytest.fixture(scope="module")
+def big(G):
+    GL, pos = H.gen_synth.synth_fast(3000, 500, 77)
+    gl, expg, maf = N.prepare_sites(GL)
+    eng = N.Engine(0)
+    eng.set_sites(gl, expg, maf)
+    eng.set_positions(np.diff(np.concatenate([[0], pos])).astype(np.float64), None)
+    yield eng, (gl, expg, maf)
+    eng.close()
+
+
+def test_large_scan_fast_vs_strict_sample_and_pass_checksum(G, big):
+    eng, arrays = big
+    P = N.ScanParams.make(max_kb_dist=0)
+    rows = eng.scan(P)                                   # 4.5 M pairs through the warp-per-pair kernel
+    st = eng.stats()
+    assert len(rows) == 3000 * 2999 // 2 and st["em_kernel"].startswith("emwarp::")
+    it = rows["n_iter"].astype(np.int64)
+    assert int(np.where(it < 100, it + 1, 100).sum()) == st["sum_em_passes"]
+    sel = np.sort(np.random.default_rng(5).choice(len(rows), 20000, replace=False))
+    strict = eng.pairs(rows["s1"][sel], rows["s2"][sel], strict=True)
+    G.assert_fast_close(rows[sel], strict)
+    # the oracle itself on a handful
+    few = sel[:40]
+    G.assert_strict_equal(strict[:40], G.oracle_rows(arrays, rows["s1"][few], rows["s2"][few]))
+    # domain invariants over the whole scan
+    hap = rows["hap"]
+    ok = np.isfinite(rows["r2"])
+    assert np.all(np.abs(hap.sum(1) - 1) < 1e-12)
+    assert np.all(np.abs(rows["Dp"][ok]) <= 1 + 1e-9) and np.all((rows["r2"][ok] >= 0) & (rows["r2"][ok] <= 1 + 1e-9))
+    assert np.all((rows["r2_expg"] >= 0) & (rows["r2_expg"] <= 1 + 1e-12))
+    assert np.all(np.diff(rows["s1"].astype(np.int64)) >= 0)       # (s1, s2) order
+
+
+def test_large_scan_shards_concatenate(big):
+    eng, _ = big
+    P = N.ScanParams.make(max_kb_dist=0, max_snp_dist=700)
+    whole = eng.scan(P)
+    b = eng.partition(P, 4)
+    parts = [eng.scan(P, int(b[k]), int(b[k + 1])) for k in range(4)]
+    assert sum(len(p) for p in parts) == len(whole)
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 2 * 700
+    assert np.concatenate(parts).tobytes() == whole.tobytes()
+
+
+def test_site_swap_symmetry(big):
+    eng, _ = big
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 3000, 5000).astype(np.uint32)
+    b = rng.integers(0, 3000, 5000).astype(np.uint32)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    for strict in (True, False):
+        x, y = eng.pairs(a, b, strict=strict), eng.pairs(b, a, strict=strict)
+        assert np.array_equal(x["n_iter"], y["n_iter"])
+        tol = 0 if strict else 1e-12
+        # swapping the sites swaps the roles of hap01 and hap10; in strict mode the arithmetic is NOT symmetric in
+        # the two sites (association order), so only the fast-kernel tolerance applies to both
+        for f, g in (("D", "D"), ("r2", "r2")):
+            fin = np.isfinite(x[f]) & np.isfinite(y[g])
+            assert np.all(np.abs(x[f][fin] - y[g][fin]) <= 1e-9)
+        assert np.all(np.abs(x["hap"][:, 1] - y["hap"][:, 2]) <= 1e-9) and np.all(np.abs(x["hap"][:, 0] - y["hap"][:, 0]) <= 1e-9)
+        assert G_same(x["r2_expg"], y["r2_expg"], 1e-12)
+
+
+def G_same(a, b, tol):
+    fin = np.isfinite(a) & np.isfinite(b)
+    return bool(np.all(np.abs(a[fin] - b[fin]) <= tol)) and bool(np.all(np.isnan(a) == np.isnan(b)))
+
+
+@pytest.mark.parametrize("n_ind,env", [(500, {"NGSLD_WARP_R": "4"}), (500, {"NGSLD_WARP_G": "2"}), (500, {"NGSLD_WARP_G": "4"}),
+                                       (500, {"NGSLD_EM_PATH": "tile"}), (500, {"NGSLD_EM_PATH": "list"}),
+                                       (1000, {}), (1000, {"NGSLD_EM_PATH": "list"}), (250, {"NGSLD_EM_PATH": "warp", "NGSLD_WARP_R": "3"}),
+                                       (90, {"NGSLD_EM_PATH": "warp"})])
+def test_every_kernel_family_agrees_with_strict(G, n_ind, env, monkeypatch):
+    GL, _ = H.gen_synth.synth_fast(160, n_ind, 1234 + n_ind)
+    gl, expg, maf = N.prepare_sites(GL)
+    with N.Engine(0) as eng:
+        eng.set_sites(gl, expg, maf)
+        strict = eng.scan(N.ScanParams.make(max_kb_dist=0, strict=1))
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for ign in (0, 1):
+            fast = eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=ign))
+            ref = strict if not ign else eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=1, strict=1))
+            G.assert_fast_close(fast, ref)
