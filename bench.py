@@ -347,8 +347,17 @@ def main():
         flop = passes * a.n_ind * 45.0
         fp64_achieved = flop / em_s / 1e9
         issue = passes * a.n_ind * 27.0 / em_s / (fp64_peak * 1e9 / 2.0) if fp64_peak else None
+        # DRAM traffic of that kernel per launch, from the committed ncu --set full capture (bytes per pair x pairs/launch)
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tj):
+            t = json.load(open(tj))
+            if t.get("kernel") == em_kernel and a.n_ind == 500:
+                traffic = t["dram_bytes_per_pair"] * pairs / n_chunks
+                traffic_src = t["source"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": em_kernel,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": bpp * pairs / n_chunks, "peak_source": peak_src, "kernel": em_kernel,
                     "algorithmic_bytes_per_pair": bpp, "launch_ms_avg": ms_em / n_chunks,
                     "launches_timed": n_chunks,
                     "note": "path is FP64-issue-bound (~%.0f EM passes/pair), not HBM-bound; see fp64" % (passes / max(1, pairs)),

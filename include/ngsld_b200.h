@@ -134,7 +134,8 @@ int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int
 
 /* ---- data upload ----------------------------------------------------------------------------- */
 /* replaces the shared read-only arrays of `params` (geno_lkl, expected_geno, maf; ngsLD.hpp:36-41):
- * copies them to the device (and derives the per-site x87 Pearson terms on the host FPU). */
+ * copies them to the device and derives the per-site x87 Pearson terms there (aux::site_terms_kernel).  Device buffers
+ * are kept when the shape is unchanged, so calling it once per batch costs only the copies. */
 int ngsld_set_sites(ngsld_ctx *ctx, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
                     uint64_t n_ind);
 /* replaces params.pos_dist / params.labels (ngsLD.cpp:119-135).  pos_dist NULL = all +inf (no --pos);

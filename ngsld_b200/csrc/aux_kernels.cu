@@ -129,6 +129,41 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-site half of the same recurrence (gsl_stats_correlation, GSL statistics/covariance_source.c, called at
+// reference ngsLD.cpp:366): for site s with expected genotypes x[0..n),
+//     mean = x[0];  for i >= 1:  delta_i = x[i] - mean;  sum_sq += delta_i * delta_i * ratio_i;  mean += delta_i / (i + 1.0)
+// all in x87 extended precision (ratio_i = i / (i + 1.0) is a double division widened).  Stores the 80-bit memory image
+// of every delta_i and q = sqrt((double)sum_sq).  One thread per site; the recurrence is sequential in i.
+__global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad,
+                                                         uint64_t *dx_sig, uint16_t *dx_se, double *q) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
+    const double *x = expg + (size_t)s * n_ind;
+    uint64_t *sig = dx_sig + (size_t)s * n_pad;
+    uint16_t *se = dx_se + (size_t)s * n_pad;
+    x87::ext mean = x87::from_double(x[0]);
+    x87::ext ssq = x87::zero(0);
+    sig[0] = 0;
+    se[0] = 0;
+    for (uint32_t i = 1; i < n_ind; i++) {
+      const double ip1 = __dadd_rn((double)i, 1.0);
+      const x87::ext ratio = x87::from_double(__ddiv_rn((double)i, ip1));
+      x87::ext neg_mean = mean;
+      neg_mean.neg ^= 1u;
+      const x87::ext delta = x87::add(x87::from_double(x[i]), neg_mean);
+      ssq = x87::add(ssq, x87::mul(x87::mul(delta, delta), ratio));
+      mean = x87::add(mean, x87::div(delta, x87::from_double(ip1)));
+      sig[i] = delta.sig;
+      se[i] = (uint16_t)((delta.neg << 15) | (delta.sig ? (uint32_t)(delta.exp + 16383) : 0u));
+    }
+    for (uint32_t i = n_ind; i < n_pad; i++) {
+      sig[i] = 0;
+      se[i] = 0;
+    }
+    q[s] = __dsqrt_rn(x87::to_double(ssq));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Window plan -> explicit pair list for output rows [row_lo, row_lo + n): row g belongs to the
 // compact first site c1 with row_off[c1] <= g < row_off[c1+1]; its partner is c1 + 1 + (g - row_off[c1]).
 __global__ void expand_window_kernel(const unsigned long long *row_off, const uint32_t *cs, uint32_t n_compact,

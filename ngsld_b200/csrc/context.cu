@@ -76,7 +76,7 @@ struct ngsld_ctx {
   std::string err;
   // sites
   uint64_t n_sites = 0, n_ind = 0, n_pad = 0;
-  double *d_gl = nullptr, *d_maf = nullptr, *d_q = nullptr;
+  double *d_gl = nullptr, *d_maf = nullptr, *d_q = nullptr, *d_expg = nullptr;
   uint64_t *d_dx_sig = nullptr;
   uint16_t *d_dx_se = nullptr;
   std::vector<double> h_maf;
@@ -846,6 +846,7 @@ void ngsld_destroy(ngsld_ctx *c) {
   cudaDeviceSynchronize();
   free_chunks(c);
   dfree(c->d_gl);
+  dfree(c->d_expg);
   dfree(c->d_maf);
   dfree(c->d_q);
   dfree(c->d_dx_sig);
@@ -913,41 +914,58 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     if (maf[s] < 0 || maf[s] > 1) return fail(c, NGSLD_E_DATA, "invalid allele frequencies");  // gen_func.cpp:1030
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
-  dfree(c->d_gl);
-  dfree(c->d_maf);
-  dfree(c->d_q);
-  dfree(c->d_dx_sig);
-  dfree(c->d_dx_se);
   dfree(c->d_cum);
-  dfree(c->d_seg);
   dfree(c->d_label_blob);
   dfree(c->d_label_off);
   c->have_pos = c->have_labels = false;
+  const uint64_t n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
+  const size_t row_bytes = n_pad * 24;
+  if (n_sites != c->n_sites || n_ind != c->n_ind || !c->d_gl) {  // same shape as last time: keep the device buffers
+    dfree(c->d_gl);
+    dfree(c->d_maf);
+    dfree(c->d_q);
+    dfree(c->d_dx_sig);
+    dfree(c->d_dx_se);
+    dfree(c->d_seg);
+    dfree(c->d_expg);
+    c->n_sites = c->n_ind = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
+    CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * n_pad * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * n_pad * sizeof(uint16_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_expg, n_sites * n_ind * sizeof(double)));
+  }
   c->n_sites = n_sites;
   c->n_ind = n_ind;
-  c->n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
-  const size_t row_bytes = c->n_pad * 24;
-  CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
-  CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * c->n_pad * sizeof(uint64_t)));
-  CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * c->n_pad * sizeof(uint16_t)));
-  CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
+  c->n_pad = n_pad;
   CUDA_TRY(c, cudaMemsetAsync(c->d_seg, 0, n_sites * sizeof(uint32_t), c->s_main));
-  if (c->n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * row_bytes, c->s_main));
+  if (n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * row_bytes, c->s_main));
   CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, row_bytes, gl, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
   CUDA_TRY(c, cudaMemcpyAsync(c->d_maf, maf, n_sites * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
   c->h_maf.assign(maf, maf + n_sites);
-  // per-site x87 terms of the expected-genotype correlation, on the host FPU
-  std::vector<uint64_t> sig(n_sites * c->n_pad);
-  std::vector<uint16_t> se(n_sites * c->n_pad);
-  std::vector<double> q(n_sites);
-  const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
-  hostprep::pearson_site_terms(expg, n_sites, n_ind, c->n_pad, nt, sig.data(), se.data(), q.data());
-  CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
-  CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
-  CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
-  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  // per-site x87 terms of the expected-genotype correlation
+  const char *host_terms = getenv("NGSLD_HOST_TERMS");
+  if (host_terms && atoi(host_terms)) {
+    // cross-check path: the host FPU's native long double instead of the device's emulation (same bits)
+    std::vector<uint64_t> sig(n_sites * n_pad);
+    std::vector<uint16_t> se(n_sites * n_pad);
+    std::vector<double> q(n_sites);
+    const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
+    hostprep::pearson_site_terms(expg, n_sites, n_ind, n_pad, nt, sig.data(), se.data(), q.data());
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  } else {
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_expg, expg, n_sites * n_ind * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_sites + 127) / 128, (uint64_t)c->sm_count * 16);
+    aux::site_terms_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_expg, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad,
+                                                          c->d_dx_sig, c->d_dx_se, c->d_q);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  }
   c->h_seg.assign(n_sites, 0);
   c->h_cum.assign(n_sites, 0.0);
   return NGSLD_OK;

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <random>
+#include <vector>
 #include "../../ngsld_b200/csrc/fp80.cuh"
 
 static x87::ext from_ld(long double v) {
@@ -59,6 +61,36 @@ int main(int argc, char **argv) {
     volatile double d = (double)a;
     double mine = x87::to_double(from_ld(a));
     if (memcmp(&mine, (const void *)&d, 8) != 0) { if (bad++ < 5) printf("subnormal narrowing mismatch e=%d\n", e); }
+  }
+  // the per-site half of gsl_stats_correlation as aux::site_terms_kernel performs it, against native long double
+  std::uniform_real_distribution<double> E(0.0, 2.0);
+  for (int rep = 0; rep < 300; rep++) {
+    const int n_ind = 2 + (int)(g() % 600);
+    std::vector<double> x(n_ind);
+    for (auto &v : x) v = (g() % 7 == 0) ? 0.0 : ((g() % 5 == 0) ? 1.0 : E(g));
+    if (rep % 17 == 0) std::fill(x.begin(), x.end(), 0.75);  // monomorphic site: every delta is exactly zero
+    volatile long double mean = x[0], ssq = 0.0L;
+    x87::ext emean = x87::from_double(x[0]), essq = x87::zero(0);
+    for (int i = 1; i < n_ind; i++) {
+      const long double ratio = i / (i + 1.0);
+      const long double delta = x[i] - mean;
+      ssq += delta * delta * ratio;
+      mean += delta / (i + 1.0);
+      const double ip1 = (double)i + 1.0;
+      const x87::ext eratio = x87::from_double((double)i / ip1);
+      x87::ext neg_mean = emean;
+      neg_mean.neg ^= 1u;
+      const x87::ext edelta = x87::add(x87::from_double(x[i]), neg_mean);
+      essq = x87::add(essq, x87::mul(x87::mul(edelta, edelta), eratio));
+      emean = x87::add(emean, x87::div(edelta, x87::from_double(ip1)));
+      if (!same(edelta, delta) || !same(emean, mean) || !same(essq, ssq)) {
+        if (bad++ < 5) printf("site recurrence mismatch rep %d i %d\n", rep, i);
+        break;
+      }
+    }
+    volatile double qn = sqrt((double)ssq);
+    double qe = sqrt(x87::to_double(essq));
+    if (memcmp(&qe, (const void *)&qn, 8) != 0) { if (bad++ < 5) printf("q mismatch rep %d\n", rep); }
   }
   printf("checked %ld random operand pairs, %ld mismatches\n", n, bad);
   return bad ? 1 : 0;
