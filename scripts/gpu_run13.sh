@@ -1,0 +1,3 @@
+nvidia-smi -L
+bash scripts/full_parity_config2.sh 10000
+(timeout 600 python -m pytest tests/test_cli.py -m gpu -x -q 2>&1 | tail -3)

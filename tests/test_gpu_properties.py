@@ -107,3 +107,20 @@ def test_every_kernel_family_agrees_with_strict(G, n_ind, env, monkeypatch):
             fast = eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=ign))
             ref = strict if not ign else eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=1, strict=1))
             G.assert_fast_close(fast, ref)
+
+
+def test_device_site_terms_equal_host_x87(monkeypatch):
+    """The per-site x87 Pearson terms computed by the emulation on the device and by the host FPU's native long
+    double give byte-identical rows."""
+    GL, _ = H.gen_synth.synth(300, 77, 31)
+    GL[5, :] = [1.0, 0.0, 0.0]          # monomorphic site: all deviations exactly zero
+    GL[9, ::2] = [0.0, 0.0, 1.0]
+    gl, expg, maf = N.prepare_sites(GL)
+    P = N.ScanParams.make(max_kb_dist=0, strict=1)
+    with N.Engine(0) as eng:
+        eng.set_sites(gl, expg, maf)
+        dev = eng.scan(P)
+        monkeypatch.setenv("NGSLD_HOST_TERMS", "1")
+        eng.set_sites(gl, expg, maf)
+        host = eng.scan(P)
+    assert dev.tobytes() == host.tobytes()
