@@ -107,12 +107,7 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
     const uint64_t *ma = T.dx_sig + (size_t)s1 * T.n_pad, *mb = T.dx_sig + (size_t)s2 * T.n_pad;
     const uint16_t *ea = T.dx_se + (size_t)s1 * T.n_pad, *eb = T.dx_se + (size_t)s2 * T.n_pad;
     x87::ext acc = x87::zero(0);
-    for (uint32_t i = 1; i < T.n_ind; i++) {
-      const x87::ext da = x87::from_bits(ma[i], ea[i]);
-      const x87::ext db = x87::from_bits(mb[i], eb[i]);
-      const x87::ext ratio = x87::from_double(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0)));
-      acc = x87::add(acc, x87::mul(x87::mul(da, db), ratio));
-    }
+    for (uint32_t i = 1; i < T.n_ind; i++) x87::mac_ratio(acc, ma[i], ea[i], mb[i], eb[i], __ldg(T.ratio + i));
     const double den = __dmul_rn(T.q[s1], T.q[s2]);
     double r;
     if (den == 0.0 || den != den) {
@@ -135,7 +130,10 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
 // all in x87 extended precision (ratio_i = i / (i + 1.0) is a double division widened).  Stores the 80-bit memory image
 // of every delta_i and q = sqrt((double)sum_sq).  One thread per site; the recurrence is sequential in i.
 __global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad,
-                                                         uint64_t *dx_sig, uint16_t *dx_se, double *q) {
+                                                         uint64_t *dx_sig, uint16_t *dx_se, double *q, uint64_t *ratio) {
+  // the ratio table shared by every pair: significand of (long double)(i / (i + 1.0))
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+    ratio[i] = i ? x87::ratio_sig(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0))) : 0ull;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
     const double *x = expg + (size_t)s * n_ind;
     uint64_t *sig = dx_sig + (size_t)s * n_pad;

@@ -14,6 +14,7 @@ struct SiteTable {
   const uint64_t *dx_sig;  // [n_sites][n_pad] x87 significand of the Pearson deviation x[i]-mean_(i-1)
   const uint16_t *dx_se;   // [n_sites][n_pad] sign|biased exponent of the same
   const double *q;         // [n_sites] sqrt((double)sum_xsq)
+  const uint64_t *ratio;   // [n_pad] x87 significand of (long double)(i / (i + 1.0)) (exponent -1); entry 0 unused
   const double *cum;       // [n_sites] exact prefix sum of finite pos_dist (NULL: no positions)
   const uint32_t *seg;     // [n_sites] chromosome segment id (increments at each +inf pos_dist)
   uint32_t n_sites, n_ind, n_pad;

@@ -77,7 +77,7 @@ struct ngsld_ctx {
   // sites
   uint64_t n_sites = 0, n_ind = 0, n_pad = 0;
   double *d_gl = nullptr, *d_maf = nullptr, *d_q = nullptr, *d_expg = nullptr;
-  uint64_t *d_dx_sig = nullptr;
+  uint64_t *d_dx_sig = nullptr, *d_ratio = nullptr;
   uint16_t *d_dx_se = nullptr;
   std::vector<double> h_maf;
   // positions / labels
@@ -178,6 +178,7 @@ SiteTable site_table(const ngsld_ctx *c) {
   T.dx_sig = c->d_dx_sig;
   T.dx_se = c->d_dx_se;
   T.q = c->d_q;
+  T.ratio = c->d_ratio;
   T.cum = c->have_pos ? c->d_cum : nullptr;
   T.seg = c->d_seg;
   T.n_sites = (uint32_t)c->n_sites;
@@ -847,6 +848,7 @@ void ngsld_destroy(ngsld_ctx *c) {
   free_chunks(c);
   dfree(c->d_gl);
   dfree(c->d_expg);
+  dfree(c->d_ratio);
   dfree(c->d_maf);
   dfree(c->d_q);
   dfree(c->d_dx_sig);
@@ -928,6 +930,7 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     dfree(c->d_dx_se);
     dfree(c->d_seg);
     dfree(c->d_expg);
+    dfree(c->d_ratio);
     c->n_sites = c->n_ind = 0;
     CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
     CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
@@ -936,6 +939,7 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * n_pad * sizeof(uint16_t)));
     CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&c->d_expg, n_sites * n_ind * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_pad * sizeof(uint64_t)));
   }
   c->n_sites = n_sites;
   c->n_ind = n_ind;
@@ -957,12 +961,13 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
+    aux::site_terms_kernel<<<8, 128, 0, c->s_main>>>(nullptr, 0, 0, (uint32_t)n_pad, nullptr, nullptr, nullptr, c->d_ratio);
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   } else {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_expg, expg, n_sites * n_ind * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
     const unsigned blocks = (unsigned)std::min<uint64_t>((n_sites + 127) / 128, (uint64_t)c->sm_count * 16);
     aux::site_terms_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_expg, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad,
-                                                          c->d_dx_sig, c->d_dx_se, c->d_q);
+                                                          c->d_dx_sig, c->d_dx_se, c->d_q, c->d_ratio);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   }

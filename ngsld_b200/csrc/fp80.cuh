@@ -219,6 +219,123 @@ X87_HD ext div(const ext &a, const ext &b) {
   return round_pack(neg, e, q, guard ? 0x8000000000000000ull : 0, rem != 0);
 }
 
+// ---- fused fast path of the r2_ExpG inner loop ---------------------------------------------------------------
+// One step of sum += fl80( fl80(a * b) * r ) with r = rsig * 2^-64 in [0.5, 1) (the ratio i/(i+1.0) of
+// gsl_stats_correlation widened to 80 bits: its exponent is always -1).  Same results as
+// add(acc, mul(mul(a, b), r)) above, with the case analysis the general routines need stripped down to what
+// this loop can see: a, b, r are zero or normal, the accumulator is never -0 (it starts at +0, +0 + -0 = +0 and an
+// exact cancellation gives +0 under round-to-nearest).
+
+// 128-bit product of two normalised significands -> rounded 64-bit significand; returns the exponent increment
+// relative to (ea + eb): 1 if the product had its top bit set, 0 otherwise, +1 if rounding carried out.
+X87_HD int32_t mul_round(uint64_t a, uint64_t b, uint64_t &out) {
+  uint64_t hi, lo;
+  mul64(a, b, hi, lo);
+  const uint32_t top = (uint32_t)(hi >> 63);
+  if (!top) {
+    hi = (hi << 1) | (lo >> 63);
+    lo <<= 1;
+  }
+  const uint64_t inc = (lo >> 63) & (uint64_t)(((lo << 1) != 0) | (hi & 1));
+  hi += inc;
+  const uint32_t carry = hi == 0;  // only an all-ones significand can wrap
+  out = hi | ((uint64_t)carry << 63);
+  return (int32_t)(top + carry);
+}
+
+X87_HD void mac_ratio(ext &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
+  if (asig == 0 || bsig == 0) return;  // a zero term leaves the (never -0) accumulator unchanged
+  uint64_t psig, tsig;
+  int32_t e = (int32_t)(ase & 0x7fff) + (int32_t)(bse & 0x7fff) - 2 * 16383;
+  e += mul_round(asig, bsig, psig);        // P = fl80(a * b)
+  e += mul_round(psig, rsig, tsig) - 1;    // T = fl80(P * r), r.exp = -1
+  const uint32_t tneg = ((ase ^ bse) >> 15) & 1u;
+  if (acc.sig == 0) {
+    acc.sig = tsig;
+    acc.exp = e;
+    acc.neg = tneg;
+    return;
+  }
+  // big = operand of larger magnitude, small the other
+  const bool swap = (e > acc.exp) || (e == acc.exp && tsig > acc.sig);
+  const uint64_t big = swap ? tsig : acc.sig, small = swap ? acc.sig : tsig;
+  const int32_t ebig = swap ? e : acc.exp;
+  const uint32_t nbig = swap ? tneg : acc.neg, nsmall = swap ? acc.neg : tneg;
+  const uint32_t d = (uint32_t)(ebig - (swap ? acc.exp : e));
+  acc.neg = nbig;
+  if (d > 65) {  // small < ulp(big)/4: it cannot move big, not even across a binade boundary when subtracting
+    acc.sig = big;
+    acc.exp = ebig;
+    return;
+  }
+  // small aligned under big as 128 bits (big = big:0); bits that fall off the window only exist for d == 65
+  uint64_t shi, slo;
+  uint32_t sticky = 0;
+  if (d < 64) {
+    shi = small >> d;
+    slo = (small << 1) << (63 - d);
+  } else if (d == 64) {
+    shi = 0;
+    slo = small;
+  } else {
+    shi = 0;
+    slo = small >> 1;
+    sticky = (uint32_t)(small & 1);
+  }
+  uint64_t hi, lo;
+  int32_t er = ebig;
+  if (nbig == nsmall) {
+    lo = slo;
+    hi = big + shi;
+    if (hi < big) {  // carry out of bit 127
+      sticky |= (uint32_t)(lo & 1);
+      lo = (lo >> 1) | (hi << 63);
+      hi = (hi >> 1) | 0x8000000000000000ull;
+      er += 1;
+    }
+  } else {
+    // big:0 - shi:slo - (sticky ? something below the window : 0)
+    const uint64_t l0 = 0 - slo;
+    uint64_t borrow = slo != 0;
+    lo = l0 - sticky;
+    borrow |= (uint64_t)(l0 < sticky);
+    hi = big - shi - borrow;
+    if ((hi | lo) == 0) {  // exact cancellation -> +0
+      acc.sig = 0;
+      acc.exp = 0;
+      acc.neg = 0;
+      return;
+    }
+    if (hi == 0) {
+      hi = lo;
+      lo = 0;
+      er -= 64;
+    }
+    const int sh = clz64(hi);
+    if (sh) {
+      hi = (hi << sh) | (lo >> (64 - sh));
+      lo <<= sh;
+      er -= sh;
+    }
+  }
+  const uint64_t inc = (lo >> 63) & (uint64_t)((((lo << 1) != 0) | sticky) | (hi & 1));
+  hi += inc;
+  const uint32_t carry = hi == 0;
+  acc.sig = hi | ((uint64_t)carry << 63);
+  acc.exp = er + (int32_t)carry;
+}
+
+// significand of (long double)(i / (i + 1.0)) for i >= 1 (the value lies in [0.5, 1): exponent -1)
+X87_HD uint64_t ratio_sig(double ratio) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t b = (uint64_t)__double_as_longlong(ratio);
+#else
+  uint64_t b;
+  __builtin_memcpy(&b, &ratio, 8);
+#endif
+  return ((b & 0xfffffffffffffull) | 0x10000000000000ull) << 11;
+}
+
 // Narrow to double with round-to-nearest-even (x87 FSTP m64); overflow -> inf, underflow -> subnormal/0.
 X87_HD double to_double(const ext &a) {
   uint64_t bits;

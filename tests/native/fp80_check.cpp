@@ -62,6 +62,34 @@ int main(int argc, char **argv) {
     double mine = x87::to_double(from_ld(a));
     if (memcmp(&mine, (const void *)&d, 8) != 0) { if (bad++ < 5) printf("subnormal narrowing mismatch e=%d\n", e); }
   }
+  // the fused accumulate step of the r2_ExpG inner loop against native long double, including long random-walk
+  // sums (cancellations, tiny terms under a large accumulator, zero terms)
+  for (int rep = 0; rep < 4000; rep++) {
+    const int n_ind = 2 + (int)(g() % 700);
+    volatile long double sum = 0.0L;
+    x87::ext acc = x87::zero(0);
+    const int mode = rep % 6;
+    for (int i = 1; i < n_ind; i++) {
+      long double da = rnd_ld(mode == 0 ? 40 : 2), db = rnd_ld(mode == 1 ? 70 : 2);
+      if (mode == 2 && i % 3 == 0) da = 0.0L;
+      if (mode == 3 && i % 2 == 0) { da = 1.0L; db = -(long double)sum / ((long double)(i / (i + 1.0))); }  // near-exact cancellation
+      if (mode == 4) { da = ldexpl(da, -(int)(g() % 140)); }
+      if (mode == 5 && i == n_ind / 2) { da = 0x1p+60L; }
+      const long double ratio = i / (i + 1.0);
+      sum += da * db * ratio;
+      const x87::ext ea = from_ld(da), eb = from_ld(db);
+      uint64_t as, bs; uint16_t ae, be;
+      long double tda = da, tdb = db;
+      memcpy(&as, &tda, 8); memcpy(&ae, (char *)&tda + 8, 2);
+      memcpy(&bs, &tdb, 8); memcpy(&be, (char *)&tdb + 8, 2);
+      x87::mac_ratio(acc, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
+      if (!same(acc, sum)) {
+        if (bad++ < 5) printf("mac_ratio mismatch rep %d mode %d i %d: %La * %La\n", rep, mode, i, da, db);
+        break;
+      }
+      (void)ea; (void)eb;
+    }
+  }
   // the per-site half of gsl_stats_correlation as aux::site_terms_kernel performs it, against native long double
   std::uniform_real_distribution<double> E(0.0, 2.0);
   for (int rep = 0; rep < 300; rep++) {
