@@ -437,7 +437,8 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch) {
     for (int k = 0; k < emwarp::warp_variants_count; k++)
       if (emwarp::warp_variants[k].r == r && emwarp::warp_variants[k].g == g) cand = &emwarp::warp_variants[k];
     if (!cand) continue;
-    const size_t sm = (size_t)emwarp::WARPS_PER_CTA * 2 * emwarp::WarpGeom::tail_slots((uint32_t)c->n_pad, g, r) * 24;
+    size_t sm = (size_t)emwarp::WARPS_PER_CTA * 2 * emwarp::WarpGeom::tail_slots((uint32_t)c->n_pad, g, r) * 24;
+    if (const char *pad = getenv("NGSLD_WARP_PAD_SMEM")) sm += (size_t)atoi(pad);  // occupancy experiments
     if (sm + 2048 > (size_t)c->smem_optin) continue;
     int o = 0;
     for (const void *fn : {cand->fn, cand->fn_ign, cand->fn_u1}) {

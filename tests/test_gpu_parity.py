@@ -174,3 +174,22 @@ def test_errors_are_reported_not_thrown(G):
         with pytest.raises(N.NgsldError):
             eng.pairs([0], [99])
         assert len(eng.scan(N.ScanParams.make(max_kb_dist=5))) == 0   # no positions: every distance is inf
+
+
+def test_empty_and_degenerate_scans(G):
+    """No pairs at all: one site, a window that excludes every pair, a maf filter that drops every site."""
+    GL, pos = H.gen_synth.synth(12, 9, 3)
+    gl, expg, maf = N.prepare_sites(GL)
+    dist = np.diff(np.concatenate([[0], pos])).astype(np.float64) + 5000.0   # every gap > 5 kb
+    with N.Engine(0) as eng:
+        eng.set_sites(gl[:1], expg[:1], maf[:1])
+        assert len(eng.scan(N.ScanParams.make(max_kb_dist=0))) == 0
+        assert eng.scan_tsv(N.ScanParams.make(max_kb_dist=0)) == N.tsv_header(False)
+        eng.set_sites(gl, expg, maf)
+        eng.set_positions(dist, None)
+        assert len(eng.scan(N.ScanParams.make(max_kb_dist=1))) == 0
+        assert len(eng.scan(N.ScanParams.make(max_kb_dist=0, min_maf=1.0))) == 0
+        assert eng.count(N.ScanParams.make(max_kb_dist=0, max_snp_dist=1)) == 11
+        two = eng.scan(N.ScanParams.make(max_kb_dist=0), 10, 12)                # the last two first sites: one pair
+        assert len(two) == 1 and (two["s1"][0], two["s2"][0]) == (10, 11)
+        assert len(eng.pairs([], [])) == 0
