@@ -418,7 +418,7 @@ struct EmChoice {
 
 // Warp-per-pair kernel: R registers-resident individuals per lane, the rest of the rows in a warp-private
 // shared-memory slice.  Used when at least 3 CTAs (12 warps) fit per SM.
-int choose_warp(ngsld_ctx *c, EmChoice &ch) {
+int choose_warp(ngsld_ctx *c, EmChoice &ch, int min_occ) {
   const char *path = getenv("NGSLD_EM_PATH");  // "warp" | "list" | "tile" for experiments
   if (path && strcmp(path, "warp") != 0) return NGSLD_OK;
   const uint64_t min_ind = path ? 1 : 160;  // below: the sub-warp group kernels waste fewer lanes
@@ -452,7 +452,7 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch) {
     }
     if (occ >= 3) break;
   }
-  if (!w || (occ < 3 && !path)) return NGSLD_OK;
+  if (!w || (occ < min_occ && !path)) return NGSLD_OK;
   ch.w = w;
   ch.warp_smem = smem;
   ch.blocks_warp = std::max(1, occ) * c->sm_count;
@@ -474,10 +474,15 @@ int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
 }
 
 int choose_em(ngsld_ctx *c, const Plan &pl, EmChoice &ch) {
-  int rcw = choose_warp(c, ch);
+  int rcw = choose_warp(c, ch, 3);
   if (rcw) return rcw;
   ch.v = pick_variant(c->n_ind);
-  if (!ch.v) return NGSLD_OK;  // falls back to the strict kernel (n_ind > 2048)
+  if (!ch.v) {
+    // samples too large for three resident CTAs of the warp kernel and for the group kernels: take the warp kernel
+    // at whatever occupancy its shared-memory slots allow (n_ind up to ~5400); beyond that the strict kernel runs
+    if (!ch.w) rcw = choose_warp(c, ch, 1);
+    return rcw;
+  }
   int occ = 0;
   CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ch.v->list_fn, std::max(emfast::CTA_THREADS, ch.v->lpg), 0));
   ch.blocks_list = std::max(1, occ) * c->sm_count;

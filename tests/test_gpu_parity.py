@@ -91,7 +91,7 @@ def test_rows_strict_bit_exact_and_fast_within_tolerance(G, fx, variant, tmp_pat
 
 
 # every (individuals-per-lane, lanes-per-group) kernel instantiation family, incl. ragged tails
-@pytest.mark.parametrize("n_ind", [1, 2, 3, 7, 24, 32, 33, 64, 65, 100, 128, 129, 250, 256, 257, 500, 513, 1000, 1025, 2047])
+@pytest.mark.parametrize("n_ind", [1, 2, 3, 7, 24, 32, 33, 64, 65, 100, 128, 129, 159, 160, 250, 256, 257, 500, 513, 1000, 1025, 2047, 2500, 5001])
 @pytest.mark.parametrize("ignore_miss", [False, True])
 def test_every_group_shape_against_oracle(G, n_ind, ignore_miss):
     n_sites = 14 if n_ind <= 256 else 8
