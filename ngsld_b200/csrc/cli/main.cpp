@@ -3,8 +3,9 @@
 // Same flags, defaults, implications and validation messages as the reference CLI (parse_args.cpp:6-29,35-59,
 // 63-132,168-183), same header and TSV bytes on --out / stdout (ngsLD.cpp:77,314-351).  The thread-pool fan-out of
 // the reference's main (ngsLD.cpp:153-198) becomes: one ngsld context per GPU, the first-site axis split into
-// equal-pair-count ranges (ngsld_partition), one host thread per GPU running ngsld_scan_tsv, shards written in range
-// order — which is the row order the reference produces with --n_threads 1.
+// equal-pair-count slabs (ngsld_partition), one host thread per GPU taking slabs in order and running ngsld_scan_tsv,
+// and a writer thread appending the finished slabs in slab order — the row order the reference produces with
+// --n_threads 1 — while the GPUs work on the next ones.
 //
 // Extra flags (distinct prefix, reference command lines stay valid):
 //   --gpu_n INT       GPUs to use (default: all visible)
@@ -19,6 +20,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -143,23 +146,6 @@ static void parse(Options &o, int argc, char **argv) {
   if (o.n_threads < 1) die(fn, "number of threads cannot be less than 1!");
 }
 
-struct Shard {
-  FILE *fh = nullptr;
-  uint64_t rows = 0, bytes = 0;
-  bool failed = false;
-};
-
-static int shard_sink(void *user, const char *bytes, uint64_t n_bytes, uint64_t n_rows) {
-  Shard *s = (Shard *)user;
-  if (fwrite(bytes, 1, n_bytes, s->fh) != n_bytes) {
-    s->failed = true;
-    return 1;
-  }
-  s->rows += n_rows;
-  s->bytes += n_bytes;
-  return 0;
-}
-
 int main(int argc, char **argv) {
   Options o;
   parse(o, argc, argv);
@@ -254,47 +240,115 @@ int main(int argc, char **argv) {
         die(fn, rcs[g] == NGSLD_E_DATA ? "invalid allele frequencies" : "failed to initialise the GPU engine!");
       }
   }
-  std::vector<uint64_t> bounds(n_gpu + 1);
-  if (ngsld_partition(ctx[0], &P, n_gpu, bounds.data()) != NGSLD_OK) {
+  // Work units: slabs of first sites with (about) the same number of rows.  GPUs take slabs in order from a shared
+  // counter; a writer thread appends finished slabs to the output in slab order, which is first-site order = the
+  // reference's --n_threads 1 row order.  The GPUs run at most `window` slabs ahead of the writer, so the text held
+  // in memory stays bounded and nothing is written twice.
+  uint64_t total_rows = 0;
+  if (ngsld_scan_count(ctx[0], 0, o.n_sites, &P, &total_rows) != NGSLD_OK) {
+    fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
+    die(fn, "failed to plan the pair scan!");
+  }
+  const uint64_t rows_per_slab = 4ull << 20;
+  const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 16);
+  std::vector<uint64_t> bounds(n_slabs + 1);
+  if (ngsld_partition(ctx[0], &P, n_slabs, bounds.data()) != NGSLD_OK) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to partition the pair space!");
   }
 
   if (o.verbose >= 1) fprintf(stderr, "==> Waiting for all threads to finish...\n");
-  std::vector<Shard> shard(n_gpu);
+  struct Slab {
+    std::string text;
+    bool done = false;
+  };
+  std::vector<Slab> slab(n_slabs);
+  std::mutex mu;
+  std::condition_variable cv;
+  int next_slab = 0, written = 0;
+  bool failed = false, write_failed = false;
+  const int window = 2 * n_gpu + 2;
+  struct PerGpu {
+    uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0;
+    double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0;
+  };
+  std::vector<PerGpu> acc(n_gpu);
+
+  std::thread writer([&]() {
+    for (;;) {
+      std::string text;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return failed || written == n_slabs || slab[written].done; });
+        if (failed || written == n_slabs) return;
+        text.swap(slab[written].text);
+      }
+      const bool ok = fwrite(text.data(), 1, text.size(), out_fh) == text.size();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ok) failed = write_failed = true;
+        written++;
+      }
+      cv.notify_all();
+    }
+  });
+  auto append_sink = [](void *user, const char *bytes, uint64_t n_bytes, uint64_t) -> int {
+    ((std::string *)user)->append(bytes, n_bytes);
+    return 0;
+  };
   std::vector<int> rcs(n_gpu, 0);
-  for (int g = 0; g < n_gpu; g++) {
-    shard[g].fh = g == 0 ? out_fh : tmpfile();
-    if (!shard[g].fh) die(fn, "cannot open temporary shard file!");
-  }
   {
     std::vector<std::thread> th;
     for (int g = 0; g < n_gpu; g++)
-      th.emplace_back([&, g]() { rcs[g] = ngsld_scan_tsv(ctx[g], bounds[g], bounds[g + 1], &P, shard_sink, &shard[g]); });
+      th.emplace_back([&, g]() {
+        for (;;) {
+          int k;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            if (failed || next_slab >= n_slabs) return;
+            k = next_slab++;
+            cv.wait(lk, [&]() { return failed || k < written + window; });
+            if (failed) return;
+          }
+          std::string text;
+          uint64_t rows = 0;
+          if (ngsld_scan_count(ctx[g], bounds[k], bounds[k + 1], &P, &rows) == NGSLD_OK)
+            text.reserve(rows * (o.extend_out ? 176 : 96) + 4096);  // typical row length; append() grows it if needed
+          const int rc = ngsld_scan_tsv(ctx[g], bounds[k], bounds[k + 1], &P, append_sink, &text);
+          ngsld_scan_stats st;
+          ngsld_get_stats(ctx[g], &st);
+          acc[g].pairs += st.n_pairs; acc[g].passes += st.sum_em_passes; acc[g].launches += st.n_launches; acc[g].slabs++;
+          acc[g].ms_device += st.ms_device_total; acc[g].ms_em += st.ms_em; acc[g].ms_pearson += st.ms_pearson;
+          acc[g].ms_format += st.ms_format;
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            if (rc) {
+              rcs[g] = rc;
+              failed = true;
+            } else {
+              slab[k].text.swap(text);
+              slab[k].done = true;
+            }
+          }
+          cv.notify_all();
+          if (rc) return;
+        }
+      });
     for (auto &t : th) t.join();
   }
+  cv.notify_all();
+  writer.join();
   for (int g = 0; g < n_gpu; g++)
     if (rcs[g]) {
       fprintf(stderr, "GPU %d: %s\n", g, ngsld_last_error(ctx[g]));
-      die(fn, shard[g].failed ? "cannot write output!" : "pair scan failed!");
+      die(fn, "pair scan failed!");
     }
-  // shards in first-site order = the reference's --n_threads 1 row order
-  std::vector<char> buf(8u << 20);
-  for (int g = 1; g < n_gpu; g++) {
-    rewind(shard[g].fh);
-    size_t n;
-    while ((n = fread(buf.data(), 1, buf.size(), shard[g].fh)) > 0)
-      if (fwrite(buf.data(), 1, n, out_fh) != n) die(fn, "cannot write output!");
-    fclose(shard[g].fh);
-  }
+  if (write_failed) die(fn, "cannot write output!");
   if (o.gpu_stats)
-    for (int g = 0; g < n_gpu; g++) {
-      ngsld_scan_stats s;
-      ngsld_get_stats(ctx[g], &s);
-      fprintf(stderr, "[gpu %d] first sites [%lu,%lu): %lu pairs, %lu EM passes, %lu launches, device %.1f ms (EM %.1f, r2_ExpG %.1f, format %.1f), %.0f pairs/s\n",
-              g, bounds[g], bounds[g + 1], s.n_pairs, s.sum_em_passes, s.n_launches, s.ms_device_total, s.ms_em, s.ms_pearson,
-              s.ms_format, s.ms_device_total > 0 ? s.n_pairs / (s.ms_device_total * 1e-3) : 0.0);
-    }
+    for (int g = 0; g < n_gpu; g++)
+      fprintf(stderr, "[gpu %d] %lu slabs of %d: %lu pairs, %lu EM passes, %lu launches, scan %.1f ms incl. waiting for the writer (EM %.1f, r2_ExpG %.1f, format %.1f), %.0f pairs/s\n",
+              g, acc[g].slabs, n_slabs, acc[g].pairs, acc[g].passes, acc[g].launches, acc[g].ms_device, acc[g].ms_em, acc[g].ms_pearson,
+              acc[g].ms_format, acc[g].ms_device > 0 ? acc[g].pairs / (acc[g].ms_device * 1e-3) : 0.0);
   if (o.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   for (auto c : ctx) ngsld_destroy(c);
   ngsld_free(label_blob);
