@@ -688,6 +688,10 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   if (P.min_maf < 0 || P.min_maf > 1) return fail(c, NGSLD_E_INVALID, "minimum allele frequency must be in [0,1]!");
   CUDA_TRY(c, cudaSetDevice(c->device));
   memset(&c->stats, 0, sizeof c->stats);
+  for (auto &b : c->buf) {  // a previous scan that failed midway may have left chunks in flight
+    if (b.pending) cudaStreamSynchronize(c->s_main), cudaStreamSynchronize(c->s_aux), cudaStreamSynchronize(c->s_copy);
+    b.pending = false;
+  }
   const double t_plan0 = now_ms();
   Plan pl;
   int rc = make_plan(plan_input(c), s1_lo, s1_hi, P, pl);
