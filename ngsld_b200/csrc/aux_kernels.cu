@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
     const unsigned long long p = base + lane;
     if (p >= C.n_pairs) continue;
     const uint32_t s1 = C.s1[p], s2 = C.s2[p];
-    const uint64_t *ma = T.dx_sig + (size_t)s1 * T.n_pad, *mb = T.dx_sig + (size_t)s2 * T.n_pad;
-    const uint16_t *ea = T.dx_se + (size_t)s1 * T.n_pad, *eb = T.dx_se + (size_t)s2 * T.n_pad;
     x87::ext acc = x87::zero(0);
-    for (uint32_t i = 1; i < T.n_ind; i++) x87::mac_ratio(acc, ma[i], ea[i], mb[i], eb[i], __ldg(T.ratio + i));
+    const uint64_t *sig = T.dx_sig + T.n_sites;  // row i = 1
+    const uint16_t *se = T.dx_se + T.n_sites;
+    for (uint32_t i = 1; i < T.n_ind; i++, sig += T.n_sites, se += T.n_sites)
+      x87::mac_ratio(acc, sig[s1], se[s1], sig[s2], se[s2], __ldg(T.ratio + i));
     const double den = __dmul_rn(T.q[s1], T.q[s2]);
     double r;
     if (den == 0.0 || den != den) {
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uin
     ratio[i] = i ? x87::ratio_sig(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0))) : 0ull;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
     const double *x = expg + (size_t)s * n_ind;
-    uint64_t *sig = dx_sig + (size_t)s * n_pad;
-    uint16_t *se = dx_se + (size_t)s * n_pad;
+    uint64_t *sig = dx_sig + s;  // individual-major: element i of site s lives at [i * n_sites + s]
+    uint16_t *se = dx_se + s;
     x87::ext mean = x87::from_double(x[0]);
     x87::ext ssq = x87::zero(0);
     sig[0] = 0;
@@ -150,12 +151,12 @@ __global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uin
       const x87::ext delta = x87::add(x87::from_double(x[i]), neg_mean);
       ssq = x87::add(ssq, x87::mul(x87::mul(delta, delta), ratio));
       mean = x87::add(mean, x87::div(delta, x87::from_double(ip1)));
-      sig[i] = delta.sig;
-      se[i] = (uint16_t)((delta.neg << 15) | (delta.sig ? (uint32_t)(delta.exp + 16383) : 0u));
+      sig[(size_t)i * n_sites] = delta.sig;
+      se[(size_t)i * n_sites] = (uint16_t)((delta.neg << 15) | (delta.sig ? (uint32_t)(delta.exp + 16383) : 0u));
     }
     for (uint32_t i = n_ind; i < n_pad; i++) {
-      sig[i] = 0;
-      se[i] = 0;
+      sig[(size_t)i * n_sites] = 0;
+      se[(size_t)i * n_sites] = 0;
     }
     q[s] = __dsqrt_rn(x87::to_double(ssq));
   }

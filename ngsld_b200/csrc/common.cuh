@@ -11,8 +11,9 @@
 struct SiteTable {
   const double *gl;        // [n_sites][n_pad][3] normal-space genotype likelihoods, rows 16-byte aligned
   const double *maf;       // [n_sites]
-  const uint64_t *dx_sig;  // [n_sites][n_pad] x87 significand of the Pearson deviation x[i]-mean_(i-1)
-  const uint16_t *dx_se;   // [n_sites][n_pad] sign|biased exponent of the same
+  const uint64_t *dx_sig;  // [n_pad][n_sites] (individual-major) x87 significand of the Pearson deviation x[i]-mean_(i-1):
+                           // the 32 pairs of a warp share s1 and have consecutive s2, so their loads coalesce
+  const uint16_t *dx_se;   // [n_pad][n_sites] sign|biased exponent of the same
   const double *q;         // [n_sites] sqrt((double)sum_xsq)
   const uint64_t *ratio;   // [n_pad] x87 significand of (long double)(i / (i + 1.0)) (exponent -1); entry 0 unused
   const double *cum;       // [n_sites] exact prefix sum of finite pos_dist (NULL: no positions)

@@ -968,6 +968,17 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     std::vector<double> q(n_sites);
     const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
     hostprep::pearson_site_terms(expg, n_sites, n_ind, n_pad, nt, sig.data(), se.data(), q.data());
+    {  // the device table is individual-major
+      std::vector<uint64_t> sig_t(sig.size());
+      std::vector<uint16_t> se_t(se.size());
+      for (uint64_t s = 0; s < n_sites; s++)
+        for (uint64_t i = 0; i < n_pad; i++) {
+          sig_t[i * n_sites + s] = sig[s * n_pad + i];
+          se_t[i * n_sites + s] = se[s * n_pad + i];
+        }
+      sig.swap(sig_t);
+      se.swap(se_t);
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
