@@ -54,6 +54,30 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return __fma_rn(y, e, y);     // y (1 + e + e^2): relative error ~ e^3 + 1 ulp
 }
 
+// Sums a0..a3 over aligned groups of GL lanes (GL = 4, 8, 16, 32); every lane of a group receives the same four
+// totals.  Transposing butterfly: the first round halves the number of values a lane carries (4 -> 2), the second
+// halves it again (2 -> 1), the remaining rounds add single values, and four shuffles hand the totals back:
+// log2(GL) + 1 additions instead of 4 log2(GL).
+template <int GL>
+__device__ __forceinline__ void group_sum4(double &a0, double &a1, double &a2, double &a3, int lane) {
+  constexpr int H = GL / 2, Q = GL / 4;
+  const bool hi = lane & H, lo = lane & Q;
+  double x0 = hi ? a2 : a0, x1 = hi ? a3 : a1;
+  const double y0 = hi ? a0 : a2, y1 = hi ? a1 : a3;
+  x0 += __shfl_xor_sync(0xffffffffu, y0, H);
+  x1 += __shfl_xor_sync(0xffffffffu, y1, H);
+  double z = lo ? x1 : x0;
+  const double w = lo ? x0 : x1;
+  z += __shfl_xor_sync(0xffffffffu, w, Q);
+#pragma unroll
+  for (int o = Q / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+  const int base = lane & ~(GL - 1);
+  a0 = __shfl_sync(0xffffffffu, z, base);
+  a1 = __shfl_sync(0xffffffffu, z, base + Q);
+  a2 = __shfl_sync(0xffffffffu, z, base + H);
+  a3 = __shfl_sync(0xffffffffu, z, base + H + Q);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -190,14 +214,8 @@ __device__ __forceinline__ void run_groups(const SiteTable &T, ngsld_pair_row *r
       acc2 = __fma_rn(i2, inv, acc2);
       acc3 = __fma_rn(i3, inv, acc3);
     }
-    // group-wide sums (xor butterflies give every lane the same bits)
-#pragma unroll
-    for (int o = GL / 2; o > 0; o >>= 1) {
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-      acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
-    }
+    // group-wide sums (every lane of the group receives the same bits)
+    group_sum4<GL>(acc0, acc1, acc2, acc3, lane);
     if (MULTI) {
       const int par = it & 1;
       if (lane == 0) {

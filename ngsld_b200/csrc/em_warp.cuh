@@ -15,7 +15,7 @@
 //     i0 = p0 u0 + p1 u1   i1 = p0 v0 + p1 v1   i2 = p1 u0 + p2 u1   i3 = p1 v0 + p2 v1        (8)
 //     s  = f0 i0 + f1 i1 + f2 i2 + f3 i3   == the reference's `sum`                             (4)
 //     a_k += i_k / s                                                                       (3 + 4)
-// and per pass once: A_k = sum over lanes of a_k (transposing butterfly: 6 adds instead of 20),
+// and per pass once: A_k = sum over lanes of a_k (transposing butterfly emfast::group_sum4: 6 adds instead of 20),
 // f_k <- f_k A_k / n_used.  f_k i_k is the reference's tmp_k / 2 and its M-step is ff/(2x), so this is
 // the same fixed-point iteration; results agree with the bit-faithful kernel to ~1e-15 at equal nIter.
 #pragma once
@@ -84,28 +84,6 @@ struct TailVec {
     accum(s0, s1, s2, s3, k0, k1, k2, k3, inv_b);
   }
 };
-
-__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-__device__ __forceinline__ double shfl_idx_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
-
-// Sums a0..a3 over the 32 lanes; every lane receives the same four totals.
-__device__ __forceinline__ void warp_sum4(double &a0, double &a1, double &a2, double &a3, int lane) {
-  const bool hi16 = lane & 16, hi8 = lane & 8;
-  double x0 = hi16 ? a2 : a0, x1 = hi16 ? a3 : a1;
-  const double y0 = hi16 ? a0 : a2, y1 = hi16 ? a1 : a3;
-  x0 += shfl_xor_d(y0, 16);
-  x1 += shfl_xor_d(y1, 16);
-  double z = hi8 ? x1 : x0;
-  const double w = hi8 ? x0 : x1;
-  z += shfl_xor_d(w, 8);
-  z += shfl_xor_d(z, 4);
-  z += shfl_xor_d(z, 2);
-  z += shfl_xor_d(z, 1);
-  a0 = shfl_idx_d(z, 0);
-  a1 = shfl_idx_d(z, 8);
-  a2 = shfl_idx_d(z, 16);
-  a3 = shfl_idx_d(z, 24);
-}
 
 // R    individuals per lane held in registers (individuals lane + 32 r, r < R)
 // IGN  --ignore_miss_data: individuals whose likelihoods are flat at either site are left out
@@ -276,7 +254,7 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, Pair
           v.template run<true>(f0, f1, f2, f3, a0, a1, a2, a3, ok_a, ok_b);
         }
       }
-      warp_sum4(a0, a1, a2, a3, lane);
+      emfast::group_sum4<32>(a0, a1, a2, a3, lane);
       if (G > 1) {
         const int par = it & 1;
         if (lane == 0) {
