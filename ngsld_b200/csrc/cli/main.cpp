@@ -242,14 +242,14 @@ int main(int argc, char **argv) {
   }
   // Work units: slabs of first sites with (about) the same number of rows.  GPUs take slabs in order from a shared
   // counter; a writer thread appends finished slabs to the output in slab order, which is first-site order = the
-  // reference's --n_threads 1 row order.  The GPUs run at most `window` slabs ahead of the writer, so the text held
+  // reference's --n_threads 1 row order.  The GPUs run at most a pool of buffers ahead of the writer, so the text held
   // in memory stays bounded and nothing is written twice.
   uint64_t total_rows = 0;
   if (ngsld_scan_count(ctx[0], 0, o.n_sites, &P, &total_rows) != NGSLD_OK) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to plan the pair scan!");
   }
-  const uint64_t rows_per_slab = 4ull << 20;
+  const uint64_t rows_per_slab = 16ull << 20;  // a scan drains its chunk pipeline at the end: keep slabs long
   const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 16);
   std::vector<uint64_t> bounds(n_slabs + 1);
   if (ngsld_partition(ctx[0], &P, n_slabs, bounds.data()) != NGSLD_OK) {
@@ -267,7 +267,9 @@ int main(int argc, char **argv) {
   std::condition_variable cv;
   int next_slab = 0, written = 0;
   bool failed = false, write_failed = false;
-  const int window = 2 * n_gpu + 2;
+  // Text buffers are recycled through a pool (no page faults on fresh memory for every slab); its size is the
+  // look-ahead window: a GPU thread that finds the pool empty waits for the writer.
+  std::vector<std::string> pool(n_gpu + 2);
   struct PerGpu {
     uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0;
     double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0;
@@ -284,10 +286,12 @@ int main(int argc, char **argv) {
         text.swap(slab[written].text);
       }
       const bool ok = fwrite(text.data(), 1, text.size(), out_fh) == text.size();
+      text.clear();  // keeps the capacity
       {
         std::lock_guard<std::mutex> lk(mu);
         if (!ok) failed = write_failed = true;
         written++;
+        pool.emplace_back(std::move(text));
       }
       cv.notify_all();
     }
@@ -303,14 +307,16 @@ int main(int argc, char **argv) {
       th.emplace_back([&, g]() {
         for (;;) {
           int k;
+          std::string text;
           {
             std::unique_lock<std::mutex> lk(mu);
+            // slabs must be claimed in order by whoever holds a buffer, or the writer could starve for the next slab
+            cv.wait(lk, [&]() { return failed || next_slab >= n_slabs || !pool.empty(); });
             if (failed || next_slab >= n_slabs) return;
             k = next_slab++;
-            cv.wait(lk, [&]() { return failed || k < written + window; });
-            if (failed) return;
+            text.swap(pool.back());
+            pool.pop_back();
           }
-          std::string text;
           uint64_t rows = 0;
           if (ngsld_scan_count(ctx[g], bounds[k], bounds[k + 1], &P, &rows) == NGSLD_OK)
             text.reserve(rows * (o.extend_out ? 176 : 96) + 4096);  // typical row length; append() grows it if needed
