@@ -249,7 +249,9 @@ int main(int argc, char **argv) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to plan the pair scan!");
   }
-  const uint64_t rows_per_slab = 16ull << 20;  // a scan drains its chunk pipeline at the end: keep slabs long
+  uint64_t rows_per_slab = 16ull << 20;  // a scan drains its chunk pipeline at the end: keep slabs long
+  if (const char *e = getenv("NGSLD_CLI_SLAB_ROWS"))  // tests: force many small slabs
+    if (atoll(e) > 0) rows_per_slab = (uint64_t)atoll(e);
   const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 16);
   std::vector<uint64_t> bounds(n_slabs + 1);
   if (ngsld_partition(ctx[0], &P, n_slabs, bounds.data()) != NGSLD_OK) {

@@ -114,3 +114,17 @@ def test_cli_fast_kernel_and_all_gpus_keep_reference_row_order(tmp_path):
         if a != b:
             for x, y in zip(fa[4:], fb[4:]):
                 assert x == y or abs(float(x) - float(y)) <= 1.000001e-6 * max(1.0, abs(float(y)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slab_rows", ["97", "1000"])
+def test_cli_many_slabs_keep_bytes_and_order(slab_rows, tmp_path):
+    """The slab queue + writer thread with far more slabs than GPUs: output must not change by a byte."""
+    v = H.MANIFEST["fixtures"]["tiny"]["variants"]["ext"]
+    args = ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--pos", TINY + ".pos"] + v["flags"]
+    out = tmp_path / "o.ld"
+    r = run_cli(args + ["--gpu_strict", "--verbose", "0", "--gpu_stats", "--out", str(out)],
+                env=dict(os.environ, NGSLD_CLI_SLAB_ROWS=slab_rows))
+    assert r.returncode == 0, r.stderr.decode()
+    assert out.read_bytes() == H.golden_bytes("tiny", "ext")
+    assert b"slabs of" in r.stderr
