@@ -33,9 +33,9 @@ struct ListFetch {
   }
 };
 
-// Register cap: like the warp-per-pair kernel, 144 (128 for IPL <= 4) so that 12-16 warps share an SM.
+// Register cap: like the warp-per-pair kernel, 152 (128 for IPL <= 4) so that 12-16 warps share an SM.
 template <int IPL, int LPG>
-__global__ void __maxnreg__(IPL <= 4 ? 128 : 144) em_list_kernel(SiteTable T, PairChunk C, int ignore_miss,
+__global__ void __maxnreg__(IPL <= 4 ? 128 : 152) em_list_kernel(SiteTable T, PairChunk C, int ignore_miss,
                                                               DevCounters *ctr) {
   __shared__ GroupScratch<LPG> scr;
   ListFetch fetch;
@@ -128,7 +128,7 @@ struct TileFetch {
 };
 
 template <int IPL, int LPG>
-__global__ void __maxnreg__(IPL <= 4 ? 128 : 144) em_tile_kernel(SiteTable T, ngsld_pair_row *rows_out, TileArgs A,
+__global__ void __maxnreg__(IPL <= 4 ? 128 : 152) em_tile_kernel(SiteTable T, ngsld_pair_row *rows_out, TileArgs A,
                                                               int ignore_miss, DevCounters *ctr) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ GroupScratch<LPG> scr;

@@ -93,10 +93,10 @@ struct TailVec {
 //      (slice = WarpGeom::slice(n_pad, G)); the G partial sums of a pass meet in shared memory behind a named
 //      barrier, and every warp of the group then performs the identical M-step.  G > 1 keeps the per-warp
 //      footprint of a 500-individual pair for samples of 1000 (G = 2) or 2000 (G = 4) individuals.
-// Register cap: 144 (R >= 5) keeps three CTAs (55 K registers) plus one CTA of the r2_ExpG kernel resident per SM;
+// Register cap: 152 (R >= 5) keeps three CTAs (58 K registers) plus one CTA of the r2_ExpG kernel (5 K) resident per SM;
 // 128 (R <= 4) allows four CTAs.
 template <int R, bool IGN, int U, int G>
-__global__ void __maxnreg__(R <= 4 ? 128 : 144) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
+__global__ void __maxnreg__(R <= 4 ? 128 : 152) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t bars[WARPS_PER_CTA];
   __shared__ double red[WARPS_PER_CTA / G][2][G][4];            // per group, double-buffered by pass parity
