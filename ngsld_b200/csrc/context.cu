@@ -557,9 +557,13 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   CUDA_TRY(c, cudaEventRecord(b.ev_p0, c->s_aux));
   {
     const bool beside_em = ch.w != nullptr && !P.strict;
-    const unsigned long long want = (n + 127) / 128;
+    // four warps per SM: with fewer, the r2_ExpG kernel (which only gets the issue slots the EM leaves) becomes the
+    // critical path (measured: 96 threads -> 22 M pairs/s, 64 -> 15.5 M, against 27 M)
+    int pth = 128;
+    if (const char *e = getenv("NGSLD_PEARSON_THREADS")) pth = std::max(32, std::min(128, atoi(e) / 32 * 32));
+    const unsigned long long want = (n + pth - 1) / pth;
     const unsigned pb = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * (beside_em ? 1 : 16));
-    aux::pearson_kernel<<<pb, 128, 0, c->s_aux>>>(T, C, c->d_ctr);
+    aux::pearson_kernel<<<pb, pth, 0, c->s_aux>>>(T, C, c->d_ctr);
     c->stats.n_launches++;
   }
   CUDA_TRY(c, cudaEventRecord(b.ev_p1, c->s_aux));
