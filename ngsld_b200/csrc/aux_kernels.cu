@@ -105,10 +105,27 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
     if (p >= C.n_pairs) continue;
     const uint32_t s1 = C.s1[p], s2 = C.s2[p];
     x87::ext acc = x87::zero(0);
+    // software-pipelined by hand: the operands of individual i + 1 are requested before individual i is accumulated,
+    // otherwise every iteration would wait out a full L2 round trip (the loop body is too branchy for the compiler
+    // to hoist the loads itself)
     const uint64_t *sig = T.dx_sig + T.n_sites;  // row i = 1
     const uint16_t *se = T.dx_se + T.n_sites;
-    for (uint32_t i = 1; i < T.n_ind; i++, sig += T.n_sites, se += T.n_sites)
-      x87::mac_ratio(acc, sig[s1], se[s1], sig[s2], se[s2], __ldg(T.ratio + i));
+    uint64_t a_sig = 0, b_sig = 0, r_sig = 0;
+    uint32_t a_se = 0, b_se = 0;
+    if (T.n_ind > 1) {
+      a_sig = sig[s1]; b_sig = sig[s2]; a_se = se[s1]; b_se = se[s2]; r_sig = __ldg(T.ratio + 1);
+    }
+    for (uint32_t i = 1; i < T.n_ind; i++) {
+      uint64_t na_sig = 0, nb_sig = 0, nr_sig = 0;
+      uint32_t na_se = 0, nb_se = 0;
+      if (i + 1 < T.n_ind) {
+        sig += T.n_sites;
+        se += T.n_sites;
+        na_sig = sig[s1]; nb_sig = sig[s2]; na_se = se[s1]; nb_se = se[s2]; nr_sig = __ldg(T.ratio + i + 1);
+      }
+      x87::mac_ratio(acc, a_sig, a_se, b_sig, b_se, r_sig);
+      a_sig = na_sig; b_sig = nb_sig; a_se = na_se; b_se = nb_se; r_sig = nr_sig;
+    }
     const double den = __dmul_rn(T.q[s1], T.q[s2]);
     double r;
     if (den == 0.0 || den != den) {
