@@ -1,14 +1,14 @@
 // Warp-per-pair fast EM (replaces haplo_freq + pair_freq_iter, reference shared/gen_func.cpp:1027-1119)
-// for sample sizes of a few hundred individuals.
+// for samples of 160 individuals and more (one warp per pair up to ~580, G = 2 or 4 warps per pair beyond).
 //
-// One warp owns one site pair for its whole EM; warps never synchronise with each other.  Each lane
+// One warp owns one site pair for its whole EM; at G = 1 warps never synchronise with each other.  Each lane
 // keeps R individuals of the pair in registers (their six genotype likelihoods p[3], q[3]); the rest of
 // the two rows (individuals [32R, n_ind)) is staged ONCE per pair into a warp-private shared-memory
 // slice by two TMA bulk copies and re-read from there on every pass with conflict-free 128-bit loads
 // (a lane owns two adjacent individuals = 48 contiguous bytes of each row).  Registers + shared memory
-// together hold the pair, so the <=100 passes never touch L2/HBM, and the register footprint stays low
-// enough for three resident warps per scheduler -- what the FP64 pipe needs to stay busy (the
-// register-only kernels of em_fast.cuh run two).
+// together hold the pair, so the <=100 passes never touch L2/HBM, and the footprint per warp (152 registers,
+// ~15 KB of shared memory for 500 individuals at R = 6) leaves three warps per scheduler resident plus one CTA
+// of the integer-only r2_ExpG kernel, which runs in the issue slots this FP64-bound kernel leaves idle.
 //
 // Per pass and individual (27 FP64 + 1 MUFU):
 //     u0 = f0 q0 + f1 q1   u1 = f2 q0 + f3 q1   v0 = f0 q1 + f1 q2   v1 = f2 q1 + f3 q2        (8)
