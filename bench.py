@@ -217,7 +217,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: ngsld_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout while the communicator is
+        # created, so file descriptor 1 points at stderr until the first collective has completed
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
