@@ -654,7 +654,8 @@ int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
   if (d.mode == MODE_TEXT) {
     if (cudaEventElapsedTime(&ms, b.ev_f0, b.ev_f1) == cudaSuccess) c->stats.ms_format += ms;
     unsigned long long bytes = b.h_text_len[0];
-    if (b.h_text_len[1] == 0) {
+    static const bool force_host = getenv("NGSLD_FORCE_HOST_FORMAT") && atoi(getenv("NGSLD_FORCE_HOST_FORMAT"));  // tests
+    if (b.h_text_len[1] == 0 && !force_host) {
       CUDA_TRY(c, cudaMemcpyAsync(b.h_text, b.d_text_out, bytes, cudaMemcpyDeviceToHost, c->s_copy));
       CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
       c->stats.d2h_bytes += bytes + 16;

@@ -271,13 +271,23 @@ int launch_format(const FormatArgs &fa, const SiteTable &T, const ngsld_pair_row
   return cudaGetLastError() == cudaSuccess ? 5 : -1;
 }
 
-int format_row_host(const ngsld_pair_row &r, const char *l1, const char *l2, double maf1, double maf2, int extend_out,
+// Every NaN the x86 reference produces on this path has its sign bit set and prints as "-nan"; the GPU's canonical
+// NaN is positive, so the sign is forced before glibc sees it.
+static inline double neg_nan(double v) { return v != v ? -__builtin_nan("") : v; }
+
+int format_row_host(const ngsld_pair_row &r0, const char *l1, const char *l2, double maf1, double maf2, int extend_out,
                     char *buf, size_t cap) {
+  ngsld_pair_row r = r0;
+  r.r2_expg = neg_nan(r.r2_expg); r.D = neg_nan(r.D); r.Dp = neg_nan(r.Dp); r.r2 = neg_nan(r.r2);
+  for (int k = 0; k < 4; k++) r.hap[k] = neg_nan(r.hap[k]);
+  r.hap_maf[0] = neg_nan(r.hap_maf[0]); r.hap_maf[1] = neg_nan(r.hap_maf[1]);
+  const double chi2 = neg_nan((double)r.chi2);
+  maf1 = neg_nan(maf1); maf2 = neg_nan(maf2);
   int n = snprintf(buf, cap, "%s\t%s\t%.0f\t%f\t%f\t%f\t%f", l1, l2, r.dist, r.r2_expg, r.D, r.Dp, r.r2);
   if (n < 0 || (size_t)n >= cap) return -1;
   if (extend_out) {
     int m = snprintf(buf + n, cap - n, "\t%lu\t%f\t%f\t%f\t%f\t%f\t%f\t%f\t%f\t%f\t%f\t%lu", (unsigned long)r.n_used, maf1,
-                     maf2, r.hap[0], r.hap[1], r.hap[2], r.hap[3], r.hap_maf[0], r.hap_maf[1], r.chi2, 0.0,
+                     maf2, r.hap[0], r.hap[1], r.hap[2], r.hap[3], r.hap_maf[0], r.hap_maf[1], chi2, 0.0,
                      (unsigned long)r.n_iter);
     if (m < 0 || (size_t)(n + m) >= cap) return -1;
     n += m;

@@ -193,3 +193,22 @@ def test_empty_and_degenerate_scans(G):
         two = eng.scan(N.ScanParams.make(max_kb_dist=0), 10, 12)                # the last two first sites: one pair
         assert len(two) == 1 and (two["s1"][0], two["s2"][0]) == (10, 11)
         assert len(eng.pairs([], [])) == 0
+
+
+@pytest.mark.parametrize("fx,variant", [("edge", "ext"), ("edge", "nopos"), ("tiny", "ext"), ("tiny", "plain")])
+def test_host_format_fallback_is_byte_identical(G, fx, variant, tmp_path_factory):
+    """The chunk-level fallback the device formatter takes for values >= 1e9 (host snprintf), forced on in a
+    subprocess: same bytes, including the -nan / inf / -0.000000 spellings of the edge fixture."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import helpers as H, gpu_helpers as G\n"
+        "v = H.MANIFEST['fixtures'][%r]['variants'][%r]\n"
+        "raw, labels, dist, opt = H.load_fixture(%r, %r, v['flags'], v['pos'], v.get('geno'))\n"
+        "eng, _ = G.engine_for(raw, opt, labels, dist)\n"
+        "sys.stdout.buffer.write(eng.scan_tsv(G.scan_params(opt, True)))\n"
+    ) % (H.ROOT, H.HERE, fx, variant, fx, str(tmp_path_factory.getbasetemp()))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, NGSLD_FORCE_HOST_FORMAT="1"))
+    assert out.returncode == 0, out.stderr.decode()
+    assert out.stdout == H.golden_bytes(fx, variant)
