@@ -76,3 +76,36 @@ def test_preprocess_rejects_nan():
     raw[1, 1, 0] = np.nan
     with pytest.raises(ValueError):
         O.preprocess(raw)
+
+
+def test_pearson_matches_independent_long_double_restatement():
+    """gsl_stats_correlation's recurrence (GSL statistics/covariance_source.c) restated a second time, in numpy's
+    x87 long double, must agree bit for bit with the oracle's C version (and therefore with the GSL stand-in the
+    reference binary was built against).  This does not prove what libgsl itself does -- it is not in this image --
+    but it removes transcription errors from the one piece of third-party arithmetic on the path."""
+    ld = np.longdouble
+    assert np.finfo(ld).nmant == 63, "needs x87 80-bit long double"
+    rng = np.random.default_rng(42)
+    for n in (2, 3, 7, 24, 100, 501):
+        for rep in range(6):
+            x = rng.uniform(0, 2, n)
+            y = np.clip(0.6 * x + rng.normal(0, 0.4, n), 0, 2)
+            if rep == 0:
+                x[:] = 0.5                       # zero variance -> 0/0
+            if rep == 1:
+                y = x.copy()                     # r = 1
+            mean_x, mean_y = ld(x[0]), ld(y[0])
+            sxx = syy = sxy = ld(0)
+            for i in range(1, n):
+                ratio = ld(i / (i + 1.0))
+                dx, dy = ld(x[i]) - mean_x, ld(y[i]) - mean_y
+                sxx += dx * dx * ratio
+                syy += dy * dy * ratio
+                sxy += dx * dy * ratio
+                mean_x += dx / ld(i + 1.0)
+                mean_y += dy / ld(i + 1.0)
+            with np.errstate(all="ignore"):
+                r = np.float64(sxy / ld(np.sqrt(np.float64(sxx)) * np.sqrt(np.float64(syy))))
+                want = r * r
+            got = O.lib().orc_pearson_r2(np.ascontiguousarray(x), np.ascontiguousarray(y), n)
+            assert (np.isnan(want) and np.isnan(got)) or np.float64(got).tobytes() == np.float64(want).tobytes(), (n, rep)
