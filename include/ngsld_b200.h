@@ -167,6 +167,20 @@ int ngsld_scan_tsv(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_s
 int ngsld_scan_device(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p);
 int ngsld_get_stats(const ngsld_ctx *ctx, ngsld_scan_stats *out);
 
+/* ---- fused consumer: LD decay bins ------------------------------------------------
+ * The binning step of the reference's downstream scripts/fit_LDdecay.R (lines 133-150) done on the device, so
+ * that the pair table never leaves it: pairs with an infinite distance are dropped (line 133: dist < max_kb_dist*1000,
+ * default Inf), dist is cut into right-closed bins (k*bin_size, (k+1)*bin_size] (line 145, R's cut()), and each of
+ * the four LD statistics is summed per bin over its finite values (lines 138, 149: Inf -> NA, mean(na.rm=TRUE)).
+ * mean = sum / n.  Sums are accumulated with floating-point atomics: reproducible to ~1e-12 relative, not bitwise. */
+typedef struct {
+  uint64_t n[4];  /* finite values of r2_ExpG, D, Dp, r2 that fell into the bin */
+  double sum[4];  /* their sums */
+} ngsld_decay_bin;
+/* bins[n_bins] is overwritten; *n_outside (may be NULL) = rows dropped (infinite distance or beyond the last bin). */
+int ngsld_scan_decay(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, double bin_size,
+                     uint64_t n_bins, ngsld_decay_bin *bins, uint64_t *n_outside);
+
 /* ---- explicit pairs: replaces direct calls of haplo_freq()/pearson_r() (gen_func.hpp:101, ngsLD.hpp:59) */
 int ngsld_pairs(ngsld_ctx *ctx, const uint32_t *s1, const uint32_t *s2, uint64_t n_pairs, int ignore_miss_data,
                 int strict, ngsld_pair_row *out);

@@ -13,6 +13,7 @@ ROW_DTYPE = np.dtype([("dist", "<f8"), ("r2_expg", "<f8"), ("D", "<f8"), ("Dp", 
                       ("hap", "<f8", (4,)), ("hap_maf", "<f8", (2,)), ("chi2", "<f4"), ("n_iter", "<u4"),
                       ("n_used", "<u4"), ("s1", "<u4"), ("s2", "<u4"), ("reserved", "<u4")], align=True)
 assert ROW_DTYPE.itemsize == 112
+DECAY_DTYPE = np.dtype([("n", "<u8", (4,)), ("sum", "<f8", (4,))])
 
 E_CODES = {-1: "NGSLD_E_INVALID", -2: "NGSLD_E_CUDA", -3: "NGSLD_E_NOMEM", -4: "NGSLD_E_DATA", -5: "NGSLD_E_SINK",
            -6: "NGSLD_E_IO"}
@@ -97,6 +98,7 @@ def load_library():
         "ngsld_scan_tsv": (i32, [vp, u64, u64, C.POINTER(ScanParams), TEXT_SINK, vp]),
         "ngsld_scan_device": (i32, [vp, u64, u64, C.POINTER(ScanParams)]),
         "ngsld_get_stats": (i32, [vp, C.POINTER(ScanStats)]),
+        "ngsld_scan_decay": (i32, [vp, u64, u64, C.POINTER(ScanParams), dbl, u64, vp, C.POINTER(u64)]),
         "ngsld_pairs": (i32, [vp, pu32, pu32, u64, i32, i32, vp]),
         "ngsld_site_seeds": (i32, [u64, u64, pu64]),
         "ngsld_plan_count": (i32, [pd, vp, u64, C.POINTER(ScanParams), u64, u64, C.POINTER(u64)]),
@@ -120,7 +122,7 @@ EXPORTED = ["ngsld_abi_version", "ngsld_device_count", "ngsld_create", "ngsld_de
             "ngsld_scan_defaults", "ngsld_scan_count", "ngsld_partition", "ngsld_scan", "ngsld_scan_into",
             "ngsld_scan_tsv", "ngsld_scan_device", "ngsld_get_stats", "ngsld_pairs", "ngsld_site_seeds",
             "ngsld_tsv_header", "ngsld_probe_fp64", "ngsld_plan_count", "ngsld_plan_partition", "ngsld_load_geno",
-            "ngsld_load_positions", "ngsld_free"]
+            "ngsld_load_positions", "ngsld_free", "ngsld_scan_decay"]
 
 
 def prepare_sites(raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,
@@ -334,6 +336,16 @@ class Engine:
         hi = self.n_sites if s1_hi is None else s1_hi
         self._check(self._lib.ngsld_scan_device(self._h, s1_lo, hi, C.byref(params)))
         return self.stats()
+
+    def scan_decay(self, params, bin_size, n_bins, s1_lo=0, s1_hi=None):
+        """ngsld_scan_decay: per-distance-bin counts and sums of r2_ExpG, D, Dp, r2 accumulated on the device.
+        Returns (bins structured array with fields n[4], sum[4], rows that fell outside every bin)."""
+        hi = self.n_sites if s1_hi is None else s1_hi
+        bins = np.zeros(n_bins, DECAY_DTYPE)
+        outside = C.c_uint64(0)
+        self._check(self._lib.ngsld_scan_decay(self._h, s1_lo, hi, C.byref(params), float(bin_size), n_bins,
+                                               bins.ctypes.data_as(C.c_void_p), C.byref(outside)))
+        return bins, outside.value
 
     def stats(self):
         st = ScanStats()

@@ -262,6 +262,54 @@ __global__ void taus_sample_kernel(const unsigned long long *site_seeds, const u
 }
 
 // ------------------------------------------------------------------------------------------------
+// LD-decay bins (the binning of the reference's scripts/fit_LDdecay.R:133-150, see ngsld_scan_decay): one thread
+// per row; rows arrive sorted by (s1, s2), so neighbouring lanes mostly hit the same bin -> lanes with equal bins
+// are combined in the warp (match.any) and one lane per distinct bin issues the atomics.
+__global__ void __launch_bounds__(256) decay_bins_kernel(const ngsld_pair_row *rows, unsigned long long n, double bin_size,
+                                                         unsigned long long n_bins, ngsld_decay_bin *bins,
+                                                         unsigned long long *outside) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long n_round = (n + 31ull) & ~31ull;  // whole warps stay together for the warp collectives
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n_round; p += stride) {
+    long long bin = -1;
+    double v[4] = {0, 0, 0, 0};
+    bool live = p < n;
+    if (live) {
+      const ngsld_pair_row r = rows[p];
+      v[0] = r.r2_expg; v[1] = r.D; v[2] = r.Dp; v[3] = r.r2;
+      if (isfinite(r.dist)) {
+        bin = (long long)ceil(r.dist / bin_size) - 1;  // right-closed bins (k*b, (k+1)*b]
+        if (bin < 0) bin = 0;
+      }
+      if (bin < 0 || (unsigned long long)bin >= n_bins) bin = -1;
+    }
+    const unsigned out_mask = __ballot_sync(0xffffffffu, live && bin < 0);
+    if (lane == 0 && out_mask) atomicAdd(outside, (unsigned long long)__popc(out_mask));
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);  // lanes of this warp with the same bin
+    const int leader = __ffs(peers) - 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool fin = bin >= 0 && isfinite(v[j]);
+      double s = fin ? v[j] : 0.0;
+      unsigned cnt = fin ? 1u : 0u;
+      // sum over the peer group: every lane walks its own peer mask (groups are disjoint)
+      double tot = 0.0;
+      unsigned tc = 0;
+      for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        tot += __shfl_sync(peers, s, src);
+        tc += __shfl_sync(peers, cnt, src);
+      }
+      if (lane == leader && bin >= 0 && tc) {
+        atomicAdd(&bins[bin].sum[j], tot);
+        atomicAdd((unsigned long long *)&bins[bin].n[j], (unsigned long long)tc);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 FMA issue-rate probe: 8 independent chains per thread.
 __global__ void fp64_probe_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

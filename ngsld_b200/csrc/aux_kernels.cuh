@@ -15,5 +15,7 @@ __global__ void taus_sample_kernel(const unsigned long long *site_seeds, const u
                                    unsigned long long *counts, const unsigned long long *row_off,
                                    unsigned long long row_base, unsigned long long row_cap, uint32_t *s1,
                                    uint32_t *s2);
+__global__ void decay_bins_kernel(const ngsld_pair_row *rows, unsigned long long n, double bin_size,
+                                  unsigned long long n_bins, ngsld_decay_bin *bins, unsigned long long *outside);
 __global__ void fp64_probe_kernel(double *out, int iters);
 }  // namespace aux

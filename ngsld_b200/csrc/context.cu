@@ -97,6 +97,12 @@ struct ngsld_ctx {
   uint2 *d_tiles = nullptr;
   size_t cap_compact = 0, cap_tiles = 0;
   DevCounters *d_ctr = nullptr;
+  // LD-decay bins (ngsld_scan_decay): when active, every chunk is folded into them on the device
+  bool decay_active = false;
+  double decay_bin_size = 0;
+  unsigned long long decay_n_bins = 0;
+  ngsld_decay_bin *d_decay_bins = nullptr;
+  unsigned long long *d_decay_outside = nullptr;
   // chunks
   uint64_t chunk_rows = 4ull << 20;
   uint64_t alloc_rows = 0;
@@ -614,6 +620,12 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   c->stats.n_launches++;
   CUDA_TRY(c, cudaEventRecord(b.ev_em1, c->s_main));
   CUDA_TRY(c, cudaStreamWaitEvent(c->s_main, b.ev_p1, 0));
+  if (c->decay_active) {
+    const unsigned db = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 8);
+    aux::decay_bins_kernel<<<db, 256, 0, c->s_main>>>(b.d_rows, n, c->decay_bin_size, c->decay_n_bins, c->d_decay_bins,
+                                                     c->d_decay_outside);
+    c->stats.n_launches++;
+  }
   if (mode == MODE_TEXT) {
     CUDA_TRY(c, cudaEventRecord(b.ev_f0, c->s_main));
     int rc = fmt::launch_format(*fa, T, b.d_rows, n, b.d_text, b.d_line_off, b.d_text_out, c->sm_count, c->s_main);
@@ -879,6 +891,8 @@ void ngsld_destroy(ngsld_ctx *c) {
   dfree(c->d_counts);
   dfree(c->d_tiles);
   dfree(c->d_ctr);
+  dfree(c->d_decay_bins);
+  dfree(c->d_decay_outside);
   for (auto &b : c->buf) {
     cudaEvent_t evs[] = {b.ev_ready, b.ev_em0, b.ev_em1, b.ev_p0, b.ev_p1, b.ev_f0, b.ev_f1, b.ev_done};
     for (auto ev : evs)
@@ -1248,6 +1262,37 @@ int ngsld_scan_device(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_
   d.text = nullptr;
   d.user = nullptr;
   return run_scan(c, s1_lo, s1_hi, p, d);
+}
+
+int ngsld_scan_decay(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, double bin_size,
+                     uint64_t n_bins, ngsld_decay_bin *bins, uint64_t *n_outside) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!bins || n_bins == 0 || !(bin_size > 0)) return fail(c, NGSLD_E_INVALID, "decay bins: need bin_size > 0 and n_bins > 0");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  dfree(c->d_decay_bins);
+  dfree(c->d_decay_outside);
+  CUDA_TRY(c, cudaMalloc(&c->d_decay_bins, n_bins * sizeof(ngsld_decay_bin)));
+  CUDA_TRY(c, cudaMalloc(&c->d_decay_outside, sizeof(unsigned long long)));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_decay_bins, 0, n_bins * sizeof(ngsld_decay_bin), c->s_main));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_decay_outside, 0, sizeof(unsigned long long), c->s_main));
+  c->decay_active = true;
+  c->decay_bin_size = bin_size;
+  c->decay_n_bins = n_bins;
+  Delivery d;
+  d.mode = MODE_DEVICE;
+  d.rows = nullptr;
+  d.text = nullptr;
+  d.user = nullptr;
+  const int rc = run_scan(c, s1_lo, s1_hi, p, d);
+  c->decay_active = false;
+  if (rc) return rc;
+  unsigned long long outside = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(bins, c->d_decay_bins, n_bins * sizeof(ngsld_decay_bin), cudaMemcpyDeviceToHost, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(&outside, c->d_decay_outside, sizeof outside, cudaMemcpyDeviceToHost, c->s_main));
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  c->stats.d2h_bytes += n_bins * sizeof(ngsld_decay_bin) + 8;
+  if (n_outside) *n_outside = outside;
+  return NGSLD_OK;
 }
 
 int ngsld_get_stats(const ngsld_ctx *c, ngsld_scan_stats *out) {

@@ -124,3 +124,32 @@ def test_device_site_terms_equal_host_x87(monkeypatch):
         eng.set_sites(gl, expg, maf)
         host = eng.scan(P)
     assert dev.tobytes() == host.tobytes()
+
+
+@pytest.mark.parametrize("bin_size,n_bins,kw", [(250.0, 400, dict(max_kb_dist=100)), (1000.0, 50, dict(max_kb_dist=0)),
+                                                (333.5, 64, dict(max_kb_dist=0, rnd_sample=0.3, seed=5))])
+def test_decay_bins_equal_numpy_binning_of_the_rows(bin_size, n_bins, kw):
+    """ngsld_scan_decay (the binning of scripts/fit_LDdecay.R done on the device) against the same binning of the
+    scanned rows in numpy: counts exact, sums to 1e-9 relative (floating-point atomics reorder the additions)."""
+    GL, pos = H.gen_synth.synth(500, 60, 8)
+    GL[7, :] = [1.0, 0.0, 0.0]                      # monomorphic site: NaN statistics must be left out per column
+    gl, expg, maf = N.prepare_sites(GL)
+    dist = np.diff(np.concatenate([[0], pos])).astype(np.float64)
+    dist[300] = np.inf                              # a chromosome change: infinite distances are dropped
+    P = N.ScanParams.make(**kw)
+    with N.Engine(0) as eng:
+        eng.set_sites(gl, expg, maf)
+        eng.set_positions(dist, None)
+        rows = eng.scan(P)
+        bins, outside = eng.scan_decay(P, bin_size, n_bins)
+    k = np.ceil(rows["dist"] / bin_size) - 1
+    inside = np.isfinite(rows["dist"]) & (k < n_bins)
+    assert outside == int((~inside).sum()) and inside.sum() > 1000
+    k = k[inside].astype(np.int64)
+    for j, f in enumerate(("r2_expg", "D", "Dp", "r2")):
+        v = rows[f][inside]
+        fin = np.isfinite(v)
+        cnt = np.bincount(k[fin], minlength=n_bins)
+        tot = np.bincount(k[fin], weights=v[fin], minlength=n_bins)
+        assert np.array_equal(bins["n"][:, j], cnt), f
+        assert np.allclose(bins["sum"][:, j], tot, rtol=1e-9, atol=1e-12), f
