@@ -109,3 +109,64 @@ def test_pearson_matches_independent_long_double_restatement():
                 want = r * r
             got = O.lib().orc_pearson_r2(np.ascontiguousarray(x), np.ascontiguousarray(y), n)
             assert (np.isnan(want) and np.isnan(got)) or np.float64(got).tobytes() == np.float64(want).tobytes(), (n, rep)
+
+
+def _random_flags(rng):
+    flags = ["--probs"]
+    flags += ["--max_kb_dist", str(int(rng.choice([0, 0, 3, 8, 20])))]
+    if rng.random() < 0.4:
+        flags += ["--max_snp_dist", str(int(rng.integers(1, 12)))]
+    if rng.random() < 0.4:
+        flags += ["--min_maf", f"{rng.uniform(0.05, 0.35):.3f}"]
+    if rng.random() < 0.4:
+        flags += ["--rnd_sample", f"{rng.uniform(0.05, 0.9):.3f}", "--seed", str(int(rng.integers(1, 100000)))]
+    if rng.random() < 0.3:
+        flags += ["--ignore_miss_data"]
+    if rng.random() < 0.3:
+        t = rng.uniform(0.5, 0.99)
+        flags += ["--call_geno", "--N_thresh", f"{rng.uniform(0.0, t):.3f}", "--call_thresh", f"{t:.3f}"]
+    if rng.random() < 0.7:
+        flags += ["--extend_out"]
+    return flags
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/ngsLD not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(14))
+def test_oracle_fuzz_against_live_reference(seed, tmp_path):
+    """Random fixtures x random flag combinations: the oracle restatement must reproduce the unmodified reference
+    binary byte for byte (--n_threads 1 order)."""
+    rng = np.random.default_rng(1000 + seed)
+    n_sites, n_ind = int(rng.integers(20, 70)), int(rng.integers(2, 30))
+    GL, pos = H.gen_synth.synth(n_sites, n_ind, 2000 + seed)
+    if seed % 3 == 0:
+        GL[rng.integers(0, n_sites), :] = [1 / 3] * 3          # a site without information
+        GL[rng.integers(0, n_sites), rng.integers(0, n_ind)] = [0.0, 0.0, 0.0]
+    if seed % 4 == 1:
+        GL[rng.integers(0, n_sites), :] = [1.0, 0.0, 0.0]      # monomorphic
+    geno = str(tmp_path / "f.glf")
+    H.gen_synth.write(geno, GL, pos)
+    if seed % 5 == 2:                                         # two chromosomes
+        lines = open(geno + ".pos").read().splitlines()
+        half = len(lines) // 2
+        lines = lines[:half] + [l.replace("chr1", "chr2") for l in lines[half:]]
+        open(geno + ".pos", "w").write("\n".join(lines) + "\n")
+    flags = _random_flags(rng)
+    ref_out = str(tmp_path / "ref.ld")
+    O.run_ref(["--geno", geno, "--n_ind", str(n_ind), "--n_sites", str(n_sites), "--pos", geno + ".pos"] + flags, ref_out)
+    opt = H.parse_flags(flags)
+    raw = np.fromfile(geno, "<f8").reshape(n_sites, n_ind, 3)
+    gl, expg, maf = O.preprocess(raw, opt["log_scale"], opt["ignore_miss"], opt["call_geno"], opt["n_thresh"], opt["call_thresh"])
+    labels, dist = O.read_pos(geno + ".pos")
+    mine = str(tmp_path / "orc.ld")
+    O.run(gl, expg, maf, dist, labels, opt["max_kb_dist"], opt["max_snp_dist"], opt["min_maf"], opt["rnd_sample"],
+          opt["seed"], opt["ignore_miss"], opt["extend_out"], out_path=mine, n_threads=2)
+    assert open(mine, "rb").read() == open(ref_out, "rb").read(), flags
+    # and the product's host preparation agrees with the oracle's on the same input
+    import ngsld_b200 as N
+    a = N.prepare_sites(raw, log_scale=opt["log_scale"], ignore_miss_data=opt["ignore_miss"], call_geno=opt["call_geno"],
+                        N_thresh=opt["n_thresh"], call_thresh=opt["call_thresh"])
+    for x, y in zip(a, (gl, expg, maf)):
+        assert x.tobytes() == y.tobytes()
+    P = N.ScanParams.make(max_kb_dist=opt["max_kb_dist"], max_snp_dist=opt["max_snp_dist"], min_maf=opt["min_maf"],
+                          rnd_sample=opt["rnd_sample"], seed=opt["seed"])
+    assert N.plan_count(maf, dist, P) == open(ref_out, "rb").read().count(b"\n") - 1
