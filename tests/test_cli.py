@@ -128,3 +128,33 @@ def test_cli_many_slabs_keep_bytes_and_order(slab_rows, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     assert out.read_bytes() == H.golden_bytes("tiny", "ext")
     assert b"slabs of" in r.stderr
+
+
+REF = os.path.join(H.ROOT, "oracle", "_ref", "ngsLD")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ngsLD not built (needs /root/reference)")
+@pytest.mark.parametrize("args", [
+    [],
+    ["--geno", TINY],
+    ["--geno", TINY, "--n_ind", "24"],
+    ["--geno", TINY, "--n_ind", "24", "--n_sites", "40"],
+    ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--max_kb_dist", "0", "--min_maf", "-0.1"],
+    ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--max_kb_dist", "0", "--rnd_sample", "1.5"],
+    ["--geno", TINY, "--n_ind", "24", "--n_sites", "39", "--max_kb_dist", "0"],
+    ["--geno", "/nonexistent/x.glf", "--n_ind", "24", "--n_sites", "40", "--max_kb_dist", "0"],
+    ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--max_kb_dist", "0", "--nonsense"],
+    ["--geno", os.path.join(H.GOLD, "tiny.geno.gz"), "--n_ind", "24", "--n_sites", "40", "--max_kb_dist", "0", "--call_geno"],
+])
+def test_fatal_errors_match_the_reference_binary(args, tmp_path):
+    """Same exit status and the same 'ERROR: [func] message' line as the unmodified reference for bad invocations
+    (all of them fail before any pair is computed, so no GPU is needed)."""
+    extra = ["--verbose", "0", "--out", str(tmp_path / "o.ld")]
+    mine = run_cli(args + extra)
+    ref = subprocess.run([REF] + args + extra, capture_output=True)
+
+    def err_line(b):
+        lines = [l for l in b.decode(errors="replace").splitlines() if l.startswith("ERROR:")]
+        return lines[0] if lines else None
+    assert mine.returncode == ref.returncode
+    assert err_line(mine.stderr) == err_line(ref.stderr)
