@@ -38,3 +38,16 @@ def test_b200_arm_needs_a_gpu():
         return
     r = subprocess.run([sys.executable, BENCH, "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_measured_peaks_lookup(tmp_path):
+    sys.path.insert(0, H.ROOT)
+    import bench
+    assert bench.measured_hbm_peak(str(tmp_path / "absent.json")) == (6650.0, "fallback (B200_PROFILING.md)")
+    p = tmp_path / "MEASURED_PEAKS.json"
+    p.write_text(json.dumps({"hbm_gbs": 6553.9, "bf16_tflops": 1637.0}))
+    assert bench.measured_hbm_peak(str(p))[0] == 6553.9
+    p.write_text(json.dumps({"peaks": [{"name": "x"}, {"hbm_gbs_sustained": 6400}]}))
+    assert bench.measured_hbm_peak(str(p))[0] == 6400.0
+    p.write_text("not json")
+    assert bench.measured_hbm_peak(str(p))[0] == 6650.0
