@@ -170,3 +170,20 @@ def test_oracle_fuzz_against_live_reference(seed, tmp_path):
     P = N.ScanParams.make(max_kb_dist=opt["max_kb_dist"], max_snp_dist=opt["max_snp_dist"], min_maf=opt["min_maf"],
                           rnd_sample=opt["rnd_sample"], seed=opt["seed"])
     assert N.plan_count(maf, dist, P) == open(ref_out, "rb").read().count(b"\n") - 1
+
+
+@pytest.mark.skipif(not os.environ.get("NGSLD_SLOW"), reason="~90 s on 8 cores: set NGSLD_SLOW=1")
+def test_oracle_reproduces_survey_t2k_digest(tmp_path):
+    """SURVEY.md App. D fixture t2k (2000 x 100, seed 1, 1 999 000 rows, --extend_out): the digest of the unmodified
+    reference's --n_threads 1 output was recorded there independently of this repository."""
+    GL, pos = H.gen_synth.synth(2000, 100, 1)
+    geno = str(tmp_path / "t2k.glf")
+    H.gen_synth.write(geno, GL, pos)
+    assert H.md5(open(geno, "rb").read()) == "c0a38c1d2f02f7d201d24f1dd957d079"
+    assert H.md5(open(geno + ".pos", "rb").read()) == "2fc7fcad38b1917a54ec61cd2bbc5cf6"
+    gl, expg, maf = O.preprocess(GL)
+    labels, dist = O.read_pos(geno + ".pos")
+    out = str(tmp_path / "t2k.ld")
+    n, _ = O.run(gl, expg, maf, dist, labels, 0, 0, 0.0, 1.0, 1, False, True, n_threads=os.cpu_count() or 4, out_path=out)
+    assert n == 1999000
+    assert H.md5(open(out, "rb").read()) == "740e0c65315d7e4d9d2cffbfba956dc4"
