@@ -106,6 +106,7 @@ struct ngsld_ctx {
   // chunks
   uint64_t chunk_rows = 4ull << 20;
   uint64_t alloc_rows = 0;
+  uint32_t alloc_slot = 0;  // bytes per TSV row slot the text buffers were sized with
   bool alloc_text = false, alloc_host = false;
   ChunkBuf buf[2];
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -150,12 +151,15 @@ void free_chunks(ngsld_ctx *c) {
     b.h_text_len = nullptr;
   }
   c->alloc_rows = 0;
+  c->alloc_slot = 0;
   c->alloc_text = c->alloc_host = false;
 }
 
 int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, uint32_t slot) {
   if (rows < 1) rows = 1;
-  if (c->alloc_rows >= rows && (!need_host || c->alloc_host) && (!need_text || c->alloc_text)) return NGSLD_OK;
+  // the text buffers are rows * slot bytes: a longer slot (extend_out, longer labels) needs new ones
+  if (c->alloc_rows >= rows && (!need_host || c->alloc_host) && (!need_text || (c->alloc_text && c->alloc_slot >= slot)))
+    return NGSLD_OK;
   free_chunks(c);
   for (auto &b : c->buf) {
     CUDA_TRY(c, cudaMalloc(&b.d_s1, rows * sizeof(uint32_t)));
@@ -174,6 +178,7 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
   c->alloc_rows = rows;
   c->alloc_host = need_host && !need_text;
   c->alloc_text = need_text;
+  c->alloc_slot = need_text ? slot : 0;
   return NGSLD_OK;
 }
 

@@ -272,11 +272,13 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 152) em_warp_kernel(SiteTable T, Pair
       // ---- M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5) ----
       A0 = f0 * a0; A1 = f1 * a1; A2 = f2 * a2; A3 = f3 * a3;
       const double n0 = A0 * inv_x, n1 = A1 * inv_x, n2 = A2 * inv_x, n3 = A3 * inv_x;
-      double eps = fabs(n0 - f0);
+      // eps starts at 0 and only a difference that compares greater raises it, as in the reference: NaN frequencies
+      // (all-missing site under --ignore_miss_data, an individual with sum == 0) leave eps at 0 and stop the EM at once
+      // with nIter = the current pass.  (fmax(NaN, NaN) = NaN would instead run all 100 passes.)
+      double eps = fmax(0.0, fabs(n0 - f0));
       eps = fmax(eps, fabs(n1 - f1));
       eps = fmax(eps, fabs(n2 - f2));
       eps = fmax(eps, fabs(n3 - f3));
-      // fmax drops NaNs; the reference's `if (d > eps)` chain also never lets a NaN difference raise eps
       f0 = n0; f1 = n1; f2 = n2; f3 = n3;
       conv = eps < NGSLD_EPS;
       if (conv || it == NGSLD_ITER_MAX - 1) break;

@@ -5,7 +5,7 @@
     python tests/golden/make_golden.py
 
 Small fixtures (edge, tiny) are committed whole (inputs + gzip'd reference TSV); the larger synthetic
-ones (s, p, q) are regenerated from gen_synth.py at test time and pinned by md5 of input and of the
+ones (s, p, q, u, v) are regenerated from gen_synth.py at test time and pinned by md5 of input and of the
 reference's output (manifest.json).
 """
 import gzip
@@ -103,7 +103,11 @@ def main():
                                    "rnd01": ["--probs", "--max_kb_dist", "0", "--rnd_sample", "0.01", "--seed", "1"],
                                    "kb20": ["--probs", "--max_kb_dist", "20", "--extend_out"]}),
                 ("p", 600, 100, 5, {"ext": VARIANTS["ext"][0]}),
-                ("q", 300, 500, 7, {"ext": VARIANTS["ext"][0]})):
+                ("q", 300, 500, 7, {"ext": VARIANTS["ext"][0]}),
+                # the multi-warp-per-pair shapes of BASELINE configs 4 and 5: banded window / random sampling
+                ("u", 300, 1000, 21, {"kb50": ["--probs", "--max_kb_dist", "50", "--extend_out"]}),
+                ("v", 300, 2000, 22, {"rnd30": ["--probs", "--max_kb_dist", "0", "--rnd_sample", "0.3", "--seed", "7",
+                                                "--extend_out"]})):
             geno = os.path.join(tmp, name + ".glf")
             GLs, poss = gen_synth.synth(n_sites, n_ind, seed)
             gen_synth.write(geno, GLs, poss)

@@ -81,13 +81,20 @@ def _condition(f):
     return kd, kr
 
 
+# Tally of the fast-kernel contract over a test session (printed by tests/conftest.py at the end of the run):
+# how many pair values were compared and how many of them needed more than the flat 1e-9 of north_star.
+SLACK = {"values": 0, "needed_slack": 0, "max_kappa_of_slack": 0.0, "max_err": 0.0, "nan_pattern_forgiven": 0}
+WELL_CONDITIONED = 1e5   # kappa below this: the quotient is as stable as its inputs, the flat 1e-9 must hold
+
+
 def assert_fast_close(got, ref, tol=1e-9):
     """north_star contract: r2_ExpG bit-exact; D, D', r2 within 1e-9 at the same iteration count.
 
     hap / hap_maf / D: absolute 1e-9 (observed ~1e-16).  D' and r2 are quotients whose denominators vanish
     for near-monomorphic pairs, so their bound is tol + kappa * 1e-15 with kappa the condition number of the
-    quotient at the reference frequencies: for every well-conditioned pair that is 1e-9 to within 1e-12;
-    only where a 1e-15 change of a frequency already moves the reference's own value does it widen."""
+    quotient at the reference frequencies.  Every value that needs more than the flat `tol` is counted in SLACK,
+    and none of them may be well conditioned (kappa <= 1e5, where kappa * 1e-15 is 1e-10 at most): only where a
+    1e-15 change of a frequency already moves the reference's own value does the bound widen."""
     assert same_bits_or_nan(got["r2_expg"], ref["r2_expg"]), "r2_expg not bit-exact"
     assert np.array_equal(got["n_iter"], ref["n_iter"]), "nIter differs"
     assert np.array_equal(got["n_used"], ref["n_used"])
@@ -97,10 +104,21 @@ def assert_fast_close(got, ref, tol=1e-9):
     for f in ("D", "Dp", "r2", "hap", "hap_maf"):
         a, b = np.asarray(got[f], np.float64), np.asarray(ref[f], np.float64)
         fin = np.isfinite(a) & np.isfinite(b)
-        allowed = tol + 1e-15 * (bound[f] if np.ndim(bound[f]) == 0 or a.ndim == 1 else bound[f][:, None])
-        allowed = np.broadcast_to(allowed, a.shape)
+        kappa = bound[f] if np.ndim(bound[f]) == 0 or a.ndim == 1 else bound[f][:, None]
+        kappa = np.broadcast_to(np.asarray(kappa, np.float64), a.shape)
+        allowed = tol + 1e-15 * kappa
         # NaN / inf patterns must agree wherever the value is well conditioned
         odd = (np.isnan(a) != np.isnan(b)) | (np.isinf(a) != np.isinf(b))
-        assert not np.any(odd & (allowed < 1e-6)), f + " NaN/inf pattern"
+        assert not np.any(odd & (kappa <= WELL_CONDITIONED)), f + " NaN/inf pattern"
+        SLACK["nan_pattern_forgiven"] += int(odd.sum())
         err = np.abs(a[fin] - b[fin])
-        assert err.size == 0 or np.all(err <= allowed[fin]), (f, float(err.max()))
+        SLACK["values"] += int(err.size)
+        if err.size == 0:
+            continue
+        over = err > tol
+        assert not np.any(over & (kappa[fin] <= WELL_CONDITIONED)), (f, "well-conditioned value beyond 1e-9", float(err[over].max()))
+        assert np.all(err <= allowed[fin]), (f, float(err.max()))
+        SLACK["needed_slack"] += int(over.sum())
+        SLACK["max_err"] = max(SLACK["max_err"], float(err.max()))
+        if over.any():
+            SLACK["max_kappa_of_slack"] = max(SLACK["max_kappa_of_slack"], float(kappa[fin][over].max()))

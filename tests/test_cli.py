@@ -85,6 +85,22 @@ def test_cli_strict_output_is_byte_identical_binary_inputs(fx, variant, tmp_path
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fx,variant", [("p", "ext"), ("q", "ext"), ("u", "kb50"), ("v", "rnd30")])
+def test_cli_strict_output_md5_at_headline_sample_sizes(fx, variant, tmp_path):
+    """n_ind = 100 / 500 / 1000 (banded) / 2000 (sampled): the CLI's file has the md5 of the unmodified reference's."""
+    d = H.MANIFEST["fixtures"][fx]
+    v = d["variants"][variant]
+    geno, pos = H.fixture_paths(fx, tmp_path)
+    out = tmp_path / "o.ld"
+    r = run_cli(["--geno", geno, "--n_ind", str(d["n_ind"]), "--n_sites", str(d["n_sites"]), "--pos", pos] + v["flags"] +
+                ["--gpu_strict", "--verbose", "0", "--out", str(out)])
+    assert r.returncode == 0, r.stderr.decode()
+    got = out.read_bytes()
+    assert got.count(b"\n") - 1 == v["rows"]
+    assert H.md5(got) == v["md5"]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(H.MANIFEST["text_cases"]))
 def test_cli_strict_output_is_byte_identical_text_inputs(name, tmp_path):
     c = H.MANIFEST["text_cases"][name]

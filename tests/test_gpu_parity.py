@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 
 SMALL = [(fx, v) for fx in ("edge", "tiny") for v in H.MANIFEST["fixtures"][fx]["variants"]]
 MID = [("s", "ext"), ("s", "rnd01"), ("s", "kb20")]
+# the headline sample sizes: p = 600 x 100 (group kernels), q = 300 x 500 (warp-per-pair kernel, one warp per pair),
+# u = 300 x 1000 banded (two warps per pair), v = 300 x 2000 randomly sampled (four warps per pair)
+BIG = [("p", "ext"), ("q", "ext"), ("u", "kb50"), ("v", "rnd30")]
 
 
 @pytest.fixture(scope="module")
@@ -30,7 +33,7 @@ def _run_tsv(G, fx, variant, tmp, strict):
         return eng.scan_tsv(G.scan_params(opt, strict)), v
 
 
-@pytest.mark.parametrize("fx,variant", SMALL + MID)
+@pytest.mark.parametrize("fx,variant", SMALL + MID + BIG)
 def test_strict_tsv_is_byte_identical_to_reference(G, fx, variant, tmp_path_factory):
     got, v = _run_tsv(G, fx, variant, tmp_path_factory.getbasetemp(), strict=True)
     gold = H.golden_bytes(fx, variant)
@@ -46,7 +49,7 @@ def _parse(tsv):
     return head, rows
 
 
-@pytest.mark.parametrize("fx,variant", SMALL + MID)
+@pytest.mark.parametrize("fx,variant", SMALL + MID + BIG)
 def test_fast_tsv_matches_reference_within_contract(G, fx, variant, tmp_path_factory):
     tmp = tmp_path_factory.getbasetemp()
     got, v = _run_tsv(G, fx, variant, tmp, strict=False)
@@ -212,3 +215,50 @@ def test_host_format_fallback_is_byte_identical(G, fx, variant, tmp_path_factory
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, NGSLD_FORCE_HOST_FORMAT="1"))
     assert out.returncode == 0, out.stderr.decode()
     assert out.stdout == H.golden_bytes(fx, variant)
+
+
+@pytest.mark.parametrize("n_ind", [40, 200, 700])
+def test_all_missing_site_under_ignore_miss_stops_at_once_like_the_reference(G, n_ind):
+    """A site whose every individual is flat gets maf = 0/0 under --ignore_miss_data; its pairs have NaN frequencies,
+    and the reference's `if (d > eps)` chain leaves eps at 0, so the EM stops in the pass that produced the NaN
+    (nIter 0).  Every kernel family must report that, not 100."""
+    GL, _ = H.gen_synth.synth(10, n_ind, 500 + n_ind)
+    GL[3, :] = [1 / 3, 1 / 3, 1 / 3]
+    GL[6, : n_ind // 2] = [1 / 3, 1 / 3, 1 / 3]          # half missing: still a valid site
+    opt = H.parse_flags(["--max_kb_dist", "0", "--ignore_miss_data"])
+    eng, arrays = G.engine_for(GL, opt)
+    assert np.isnan(arrays[2][3])
+    s1, s2 = np.triu_indices(10, 1)
+    ref = G.oracle_rows(arrays, s1, s2, True)
+    touched = (s1 == 3) | (s2 == 3)
+    assert np.all(ref["n_iter"][touched] == 0) and np.all(np.isnan(ref["hap"][touched]))
+    with eng:
+        G.assert_strict_equal(eng.pairs(s1, s2, True, strict=True), ref)
+        fast = eng.scan(G.scan_params(opt, False))
+        G.assert_fast_close(fast, ref)
+        assert eng.stats()["sum_em_passes"] == int(np.where(ref["n_iter"] < 100, ref["n_iter"] + 1, 100).sum())
+
+
+def test_text_buffers_follow_the_row_slot_size(G, tmp_path_factory):
+    """One context, text scans with growing row slots: plain -> --extend_out -> longer labels.  The text buffers must
+    be re-sized with the slot (they used to be kept whenever the row count fitted)."""
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"]["s"]["variants"]["ext"]
+    raw, labels, dist, opt = H.load_fixture("s", tmp, v["flags"], True)
+    eng, _ = G.engine_for(raw, opt, None, dist)            # "(null)" labels first
+    with eng:
+        opt_plain = dict(opt, extend_out=False)
+        a = eng.scan_tsv(G.scan_params(opt_plain, True))
+        b = eng.scan_tsv(G.scan_params(opt, True))
+        eng.set_positions(dist, labels)
+        c = eng.scan_tsv(G.scan_params(opt, True))
+        long_labels = [l + ":" + "x" * 40 for l in labels]
+        eng.set_positions(dist, long_labels)
+        d = eng.scan_tsv(G.scan_params(opt, True))
+    assert H.md5(c) == v["md5"]
+    assert a.count(b"\n") == b.count(b"\n") == c.count(b"\n") == d.count(b"\n") == v["rows"] + 1
+    assert b.replace(b"(null)", b"") != b and len(b) > len(a)
+    short = c.decode().splitlines()[1:]
+    for la, lb in zip(short[:200], d.decode().splitlines()[1:201]):
+        fa, fb = la.split("\t"), lb.split("\t")
+        assert fb[0] == fa[0] + ":" + "x" * 40 and fb[1] == fa[1] + ":" + "x" * 40 and fa[2:] == fb[2:]
