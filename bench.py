@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
+CHUNK_ROWS = 4 << 20  # rows per device chunk (the library's default): one EM-kernel launch per chunk
 METRIC = "snp_pairs_per_sec"
 UNIT = "pairs/s"
 
@@ -52,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--strict", action="store_true", help="bit-faithful EM kernel instead of the fast one")
+    ap.add_argument("--em-path", default="", choices=["", "cell", "warp", "list", "tile"],
+                    help="force an EM kernel family (default: the library's choice; 'warp' = dense warp-per-pair kernel)")
     return ap.parse_args()
 
 
@@ -236,6 +239,8 @@ def main():
     import torch
     import torch.distributed as dist
     import ngsld_b200 as N
+    if a.em_path:
+        os.environ["NGSLD_EM_PATH"] = a.em_path
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -290,7 +295,7 @@ def main():
         eng.scan_device(P, cal[0], cal[1])
         st = eng.scan_device(P, cal[0], cal[1])
         rate = st["n_pairs"] / (st["ms_device_total"] * 1e-3)
-        batch = int(min(max(rate * (0.25 if a.strict else 1.5), 2_000_000), 64_000_000))
+        batch = int(min(max(rate * (0.25 if a.strict else 1.5), 2_000_000), 96_000_000))
         if world > 1:
             t = torch.tensor([batch], device="cuda", dtype=torch.int64)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -310,7 +315,8 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     ev0.record(stream)
-    pairs = launches = passes = 0
+    pairs = launches = passes = n_chunks = 0
+    cell_pairs = cells = cell_passes = resid_pairs = 0
     ms_em = ms_pearson = 0.0
     em_kernel = ""
     for k in range(a.warmup, n_steps):
@@ -321,6 +327,11 @@ def main():
         passes += st["sum_em_passes"]
         ms_em += st["ms_em"]
         ms_pearson += st["ms_pearson"]
+        n_chunks += -(-st["n_pairs"] // CHUNK_ROWS)
+        cell_pairs += st["n_cell_pairs"]
+        cells += st["sum_cells"]
+        cell_passes += st["sum_cell_passes"]
+        resid_pairs += st["n_resid_pairs"]
     ev1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -370,20 +381,30 @@ def main():
         em_s = ms_em * 1e-3
         achieved = pairs * bpp / em_s / 1e9
         hbm_peak, peak_src = measured_hbm_peak(os.path.join(ROOT, "MEASURED_PEAKS.json"))
-        # FP64 work that actually bounds the kernel, per (individual, EM pass): 9 DMUL + 18 DFMA (+ 1 MUFU seed)
-        # = 27 FP64 instructions = 45 flop [em_warp.cuh header; SURVEY.md §8(d) rounds this to 40]
-        n_chunks = max(1, launches // 4)  # expand, fill, r2_ExpG, EM per chunk
-        flop = passes * a.n_ind * 45.0
+        # FP64 work that actually bounds the kernel.  Dense kernels: per (individual, EM pass) 9 DMUL + 18 DFMA (+ 1 MUFU
+        # seed) = 27 FP64 instructions = 45 flop [em_warp.cuh header; SURVEY.md §8(d) rounds this to 40].  Class-compressed
+        # kernel: the same E-step once per CELL (distinct likelihood combination of the pair) plus one DMUL for the
+        # cell's weight = 28 instructions = 46 flop per (cell, pass); pairs it left to the dense kernel count as dense.
+        n_chunks = max(1, n_chunks)
+        cell_mode = cell_pairs > 0
+        if cell_mode:
+            dense_passes = passes * (resid_pairs / max(1, pairs))  # left-over pairs: assume the mean pass count
+            fp64_instr = cell_passes * 28.0 + dense_passes * a.n_ind * 27.0
+            flop = cell_passes * 46.0 + dense_passes * a.n_ind * 45.0
+        else:
+            fp64_instr = passes * a.n_ind * 27.0
+            flop = passes * a.n_ind * 45.0
         fp64_achieved = flop / em_s / 1e9
-        issue = passes * a.n_ind * 27.0 / em_s / (fp64_peak * 1e9 / 2.0) if fp64_peak else None
+        issue = fp64_instr / em_s / (fp64_peak * 1e9 / 2.0) if fp64_peak else None
         # DRAM traffic of that kernel per launch, from the committed ncu --set full capture (bytes per pair x pairs/launch)
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tj):
-            t = json.load(open(tj))
-            if t.get("kernel") == em_kernel and a.n_ind == 500:
-                traffic = t["dram_bytes_per_pair"] * pairs / n_chunks
-                traffic_src = t["source"]
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            tj = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tj) and traffic is None:
+                t = json.load(open(tj))
+                if t.get("kernel") == em_kernel and a.n_ind == t.get("n_ind", 500):
+                    traffic = t["dram_bytes_per_pair"] * pairs / n_chunks
+                    traffic_src = t["source"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": bpp * pairs / n_chunks, "peak_source": peak_src, "kernel": em_kernel,
@@ -397,7 +418,14 @@ def main():
                                             "this run); DFMAs reading 3 distinct registers issue at 0.73 of it "
                                             "(scripts/micro/fp64_ops.cu)",
                              "flop_per_ind_pass": 45, "fp64_instr_per_ind_pass": 27,
+                             "flop_per_cell_pass": 46, "fp64_instr_per_cell_pass": 28,
                              "mean_em_passes_per_pair": passes / max(1, pairs)}}
+        if cell_mode:
+            roofline["cells"] = {"pairs_on_cell_kernel": cell_pairs, "pairs_left_to_dense_kernel": resid_pairs,
+                                 "mean_cells_per_pair": cells / max(1, cell_pairs), "individuals": a.n_ind,
+                                 "note": "class-compressed EM: one weighted E-step per distinct (p, q) likelihood "
+                                         "combination of a pair instead of one per individual; r2_ExpG (x87 emulation, "
+                                         "integer pipes) runs inside the same kernel"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NGSLD_ABI_VERSION 1
+#define NGSLD_ABI_VERSION 2
 
 /* error codes (the reference instead prints "ERROR: [func] msg" and exit(-1), shared/gen_func.cpp:12-18) */
 #define NGSLD_OK 0
@@ -82,7 +82,10 @@ typedef struct {
   double ms_device_total;  /* first launch -> last result byte in host memory          */
   double ms_plan;          /* host planning (windows, sampling)                       */
   uint64_t h2d_bytes, d2h_bytes;
-  char em_kernel[64];      /* EM kernel family the scan used, e.g. "emwarp::em_warp_kernel<R=6,G=1>" */
+  char em_kernel[64];      /* EM kernel family the scan used, e.g. "emcell::em_cell_kernel<R=6,FUSE=1>" */
+  /* class-compressed EM (0 when another kernel family ran): pairs it computed, sum over them of distinct
+   * (p, q) combinations ("cells"), sum of cells x passes, and pairs it left to the dense kernel */
+  uint64_t n_cell_pairs, sum_cells, sum_cell_passes, n_resid_pairs;
 } ngsld_scan_stats;
 
 /* sinks: called on the scanning host thread, rows in (s1, s2) order — the order the reference

@@ -46,7 +46,8 @@ class ScanStats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("sum_em_passes", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_em", C.c_double), ("ms_pearson", C.c_double), ("ms_format", C.c_double),
                 ("ms_device_total", C.c_double), ("ms_plan", C.c_double), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("em_kernel", C.c_char * 64)]
+                ("d2h_bytes", C.c_uint64), ("em_kernel", C.c_char * 64), ("n_cell_pairs", C.c_uint64),
+                ("sum_cells", C.c_uint64), ("sum_cell_passes", C.c_uint64), ("n_resid_pairs", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

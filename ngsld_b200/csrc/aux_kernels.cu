@@ -2,6 +2,7 @@
 // window -> pair-list expansion, per-site taus sampling, and an FP64 issue-rate probe.
 #include "aux_kernels.cuh"
 #include "fp80.cuh"
+#include "pearson.cuh"
 
 namespace aux {
 
@@ -85,12 +86,7 @@ __global__ void __launch_bounds__(128) em_strict_kernel(SiteTable T, PairChunk C
 }
 
 // ------------------------------------------------------------------------------------------------
-// r2_ExpG: the pair-dependent part of gsl_stats_correlation's recurrence (reference ngsLD.cpp:365-367;
-// GSL statistics/covariance_source.c) in emulated x87 arithmetic.  Per site the host FPU already
-// produced delta_i = x_i - mean_(i-1) (80-bit) and q = sqrt((double)sum_sq); here
-//     sum_cross = sum_{i>=1} fl80( fl80(da_i * db_i) * (long double)(i/(i+1.0)) )   (in order)
-//     r = fl80( sum_cross / (long double)(qa*qb) ),  r2 = (double)r * (double)r.
-// One thread per pair; the sum is inherently sequential.
+// r2_ExpG (reference ngsLD.cpp:365-367): pearson::pair_r2 (pearson.cuh), one thread per pair.
 __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
   // Persistent: each warp repeatedly claims 32 consecutive pairs.  The launch is sized to ONE small CTA per SM when
   // the warp-per-pair EM kernel runs beside it: that kernel is bound by the FP64 pipe and leaves integer issue slots
@@ -103,41 +99,7 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
     if (base >= C.n_pairs) break;
     const unsigned long long p = base + lane;
     if (p >= C.n_pairs) continue;
-    const uint32_t s1 = C.s1[p], s2 = C.s2[p];
-    x87::ext acc = x87::zero(0);
-    // software-pipelined by hand: the operands of individual i + 1 are requested before individual i is accumulated,
-    // otherwise every iteration would wait out a full L2 round trip (the loop body is too branchy for the compiler
-    // to hoist the loads itself)
-    const uint64_t *sig = T.dx_sig + T.n_sites;  // row i = 1
-    const uint16_t *se = T.dx_se + T.n_sites;
-    uint64_t a_sig = 0, b_sig = 0, r_sig = 0;
-    uint32_t a_se = 0, b_se = 0;
-    if (T.n_ind > 1) {
-      a_sig = sig[s1]; b_sig = sig[s2]; a_se = se[s1]; b_se = se[s2]; r_sig = __ldg(T.ratio + 1);
-    }
-    for (uint32_t i = 1; i < T.n_ind; i++) {
-      uint64_t na_sig = 0, nb_sig = 0, nr_sig = 0;
-      uint32_t na_se = 0, nb_se = 0;
-      if (i + 1 < T.n_ind) {
-        sig += T.n_sites;
-        se += T.n_sites;
-        na_sig = sig[s1]; nb_sig = sig[s2]; na_se = se[s1]; nb_se = se[s2]; nr_sig = __ldg(T.ratio + i + 1);
-      }
-      x87::mac_ratio(acc, a_sig, a_se, b_sig, b_se, r_sig);
-      a_sig = na_sig; b_sig = nb_sig; a_se = na_se; b_se = nb_se; r_sig = nr_sig;
-    }
-    const double den = __dmul_rn(T.q[s1], T.q[s2]);
-    double r;
-    if (den == 0.0 || den != den) {
-      // x87: 0/0 -> default NaN; finite/0 -> signed infinity
-      if (acc.sig == 0 || den != den)
-        r = __longlong_as_double(0xfff8000000000000ll);
-      else
-        r = __longlong_as_double(acc.neg ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
-    } else {
-      r = x87::to_double(x87::div(acc, x87::from_double(den)));
-    }
-    C.rows[p].r2_expg = __dmul_rn(r, r);
+    C.rows[p].r2_expg = pearson::pair_r2(T, C.s1[p], C.s2[p]);
   }
 }
 

@@ -18,8 +18,15 @@ struct SiteTable {
   const uint64_t *ratio;   // [n_pad] x87 significand of (long double)(i / (i + 1.0)) (exponent -1); entry 0 unused
   const double *cum;       // [n_sites] exact prefix sum of finite pos_dist (NULL: no positions)
   const uint32_t *seg;     // [n_sites] chromosome segment id (increments at each +inf pos_dist)
-  uint32_t n_sites, n_ind, n_pad;
+  // site palettes (em_cell.cuh): the DISTINCT genotype-likelihood triples of a site and, per individual, which one it has
+  const uint8_t *cls;      // [n_sites][n_cpad] class of individual i = index of its triple in the site's palette
+  const double *pal;       // [n_sites][NGSLD_KMAX][3] palette, classes in order of first appearance
+  const uint8_t *pal_k;    // [n_sites] number of classes; 0 = more than NGSLD_KMAX distinct triples (site not coded)
+  const uint64_t *pal_miss;  // [n_sites] bit c set: class c is "missing data" (flat triple, gl_missing)
+  uint32_t n_sites, n_ind, n_pad, n_cpad;
 };
+
+#define NGSLD_KMAX 64  // classes per site palette (joint classes of a pair index a 64 x 64 table of 16-bit counts)
 
 // One chunk of output rows: pair p (0-based inside the chunk) is (s1[p], s2[p]) -> rows[p].
 struct PairChunk {
@@ -29,12 +36,18 @@ struct PairChunk {
 };
 
 // Counters a scan accumulates on the device.  The first NGSLD_WORK_COUNTERS fields are reset per chunk.
-#define NGSLD_WORK_COUNTERS 3
+#define NGSLD_WORK_COUNTERS 5
 struct DevCounters {
-  unsigned long long next_pair;     // dynamic work counter (list / warp EM kernels)
+  unsigned long long next_pair;     // dynamic work counter (list / warp / cell EM kernels)
   unsigned long long next_tile;     // dynamic work counter (tile kernel)
   unsigned long long next_pearson;  // dynamic work counter (r2_ExpG kernel)
-  unsigned long long em_passes;   // total EM passes executed
+  unsigned long long next_resid;    // dynamic work counter of the dense kernel over the cell kernel's left-over pairs
+  unsigned long long n_resid;       // pairs of this chunk the cell kernel handed to the dense kernel
+  unsigned long long em_passes;     // total EM passes executed
+  unsigned long long cell_passes;   // sum over pairs of (weighted cells x passes) executed by the cell kernel
+  unsigned long long cells;         // sum over pairs of weighted cells (cell kernel)
+  unsigned long long cell_pairs;    // pairs the cell kernel computed itself
+  unsigned long long resid_pairs;   // pairs handed to the dense kernel (whole scan)
 };
 
 // ---- arithmetic in the reference's operation order (no contraction) -----------------------------

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "em_cell.cuh"
 #include "em_kernels.cuh"
 #include "em_warp.cuh"
 #include "format.cuh"
@@ -42,6 +43,7 @@ double now_ms() {
 
 struct ChunkBuf {
   uint32_t *d_s1 = nullptr, *d_s2 = nullptr;
+  uint32_t *d_resid = nullptr;       // pairs of the chunk the cell kernel left to the dense kernel
   ngsld_pair_row *d_rows = nullptr;
   ngsld_pair_row *h_rows = nullptr;  // pinned
   char *d_text = nullptr;            // formatted TSV bytes (slots, then compacted)
@@ -80,6 +82,16 @@ struct ngsld_ctx {
   uint64_t *d_dx_sig = nullptr, *d_ratio = nullptr;
   uint16_t *d_dx_se = nullptr;
   std::vector<double> h_maf;
+  // site palettes + what they say about the data set (em_cell.cuh)
+  uint64_t n_cpad = 0;
+  uint8_t *d_cls = nullptr, *d_pal_k = nullptr;
+  double *d_pal = nullptr;
+  uint64_t *d_pal_miss = nullptr;
+  unsigned long long *d_cell_stats = nullptr;  // 3 counters + 129 histogram buckets (as 32-bit)
+  bool cell_ok = false;        // the class-compressed EM pays for this data set
+  bool cell_possible = false;  // palettes exist (NGSLD_EM_PATH=cell can force the kernel)
+  double cell_mean = 0, cell_uncoded_frac = 0;
+  uint32_t cell_p995 = 0;      // 99.5 % of the sampled pairs have at most this many cells
   // positions / labels
   bool have_pos = false;
   std::vector<double> h_cum;
@@ -139,6 +151,7 @@ void free_chunks(ngsld_ctx *c) {
   for (auto &b : c->buf) {
     dfree(b.d_s1);
     dfree(b.d_s2);
+    dfree(b.d_resid);
     dfree(b.d_rows);
     dfree(b.d_text);
     dfree(b.d_text_out);
@@ -164,6 +177,7 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
   for (auto &b : c->buf) {
     CUDA_TRY(c, cudaMalloc(&b.d_s1, rows * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&b.d_s2, rows * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&b.d_resid, rows * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&b.d_rows, rows * sizeof(ngsld_pair_row)));
     if (need_host && !need_text) CUDA_TRY(c, cudaMallocHost(&b.h_rows, rows * sizeof(ngsld_pair_row)));
     if (need_text) {
@@ -192,6 +206,11 @@ SiteTable site_table(const ngsld_ctx *c) {
   T.ratio = c->d_ratio;
   T.cum = c->have_pos ? c->d_cum : nullptr;
   T.seg = c->d_seg;
+  T.cls = c->d_cls;
+  T.pal = c->d_pal;
+  T.pal_k = c->d_pal_k;
+  T.pal_miss = c->d_pal_miss;
+  T.n_cpad = (uint32_t)c->n_cpad;
   T.n_sites = (uint32_t)c->n_sites;
   T.n_ind = (uint32_t)c->n_ind;
   T.n_pad = (uint32_t)c->n_pad;
@@ -425,12 +444,19 @@ struct EmChoice {
   uint32_t TA = 0, TB = 0;
   size_t dyn_smem = 0;
   int blocks_list = 0, blocks_tile = 0;
+  // class-compressed kernel (em_cell.cuh); the dense warp kernel `w` then takes the pairs it leaves over
+  const emcell::CellVariant *cell = nullptr;
+  uint32_t cell_tcap = 0;
+  size_t cell_smem = 0;
+  int blocks_cell = 0;
+  bool cell_fuse = true;
 };
 
 // Warp-per-pair kernel: R registers-resident individuals per lane, the rest of the rows in a warp-private
 // shared-memory slice.  Used when at least 3 CTAs (12 warps) fit per SM.
-int choose_warp(ngsld_ctx *c, EmChoice &ch, int min_occ) {
-  const char *path = getenv("NGSLD_EM_PATH");  // "warp" | "list" | "tile" for experiments
+int choose_warp(ngsld_ctx *c, EmChoice &ch, int min_occ, bool forced = false) {
+  const char *path = getenv("NGSLD_EM_PATH");  // "cell" | "warp" | "list" | "tile" for experiments
+  if (forced) path = "warp";
   if (path && strcmp(path, "warp") != 0) return NGSLD_OK;
   const uint64_t min_ind = path ? 1 : 160;  // below: the sub-warp group kernels waste fewer lanes
   if (c->n_ind < min_ind) return NGSLD_OK;
@@ -470,12 +496,16 @@ int choose_warp(ngsld_ctx *c, EmChoice &ch, int min_occ) {
   return NGSLD_OK;
 }
 
-int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss) {
+// sel != NULL: only the pairs sel[0 .. d_ctr->n_resid) (the cell kernel's left-overs, counted on the device)
+int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss,
+                const uint32_t *sel = nullptr) {
   SiteTable Tt = T;
   PairChunk Cc = C;
   DevCounters *ctr = c->d_ctr;
-  void *args[] = {&Tt, &Cc, &ctr};
+  const unsigned long long *n_sel = sel ? &c->d_ctr->n_resid : nullptr;
+  void *args[] = {&Tt, &Cc, &ctr, &sel, &n_sel};
   const unsigned long long want = (C.n_pairs + emwarp::WARPS_PER_CTA - 1) / emwarp::WARPS_PER_CTA;
+  // (the number of left-overs is only known on the device: CTAs that find nothing to do exit at once)
   const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_warp);
   const char *u1 = getenv("NGSLD_WARP_U1");  // experiments: unfused tail loop
   const void *fn = ignore_miss ? ch.w->fn_ign : (u1 && atoi(u1) ? ch.w->fn_u1 : ch.w->fn);
@@ -484,8 +514,68 @@ int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
   return NGSLD_OK;
 }
 
+// The class-compressed kernel on a chunk, then the dense kernel on whatever it left over (same stream).
+int launch_cell(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss, uint32_t *d_resid) {
+  SiteTable Tt = T;
+  PairChunk Cc = C;
+  DevCounters *ctr = c->d_ctr;
+  emcell::CellArgs A;
+  A.resid = d_resid;
+  A.tcap = ch.cell_tcap;
+  A.ignore_miss = ignore_miss;
+  A.fuse_pearson = ch.cell_fuse ? 1 : 0;
+  void *args[] = {&Tt, &Cc, &A, &ctr};
+  const unsigned long long want = (C.n_pairs + 32ull * emcell::WARPS_PER_CTA - 1) / (32ull * emcell::WARPS_PER_CTA);
+  const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_cell);
+  CUDA_TRY(c, cudaLaunchKernel(ch.cell_fuse ? ch.cell->fn_fused : ch.cell->fn, dim3(blocks), dim3(emcell::CTA_THREADS), args,
+                               ch.cell_smem, c->s_main));
+  c->stats.n_launches++;
+  return launch_warp(c, ch, T, C, ignore_miss, d_resid);
+}
+
+// Class-compressed kernel: used when the palettes say a pair has clearly fewer distinct (p, q) combinations than
+// individuals (ngsld_set_sites samples that), or when NGSLD_EM_PATH=cell forces it.
+int choose_cell(ngsld_ctx *c, EmChoice &ch) {
+  const char *path = getenv("NGSLD_EM_PATH");
+  if (path && strcmp(path, "cell") != 0) return NGSLD_OK;
+  if (!(path ? c->cell_possible : c->cell_ok)) return NGSLD_OK;
+  // cells per lane in registers from the sampled 99.5th percentile; the rest of a pair's cells go to shared memory
+  int r = c->cell_p995 <= 64 ? 2 : c->cell_p995 <= 128 ? 4 : 6;
+  if (const char *e = getenv("NGSLD_CELL_R")) r = atoi(e);
+  const emcell::CellVariant *v = nullptr;
+  for (int k = 0; k < emcell::cell_variants_count; k++)
+    if (emcell::cell_variants[k].r == r) v = &emcell::cell_variants[k];
+  if (!v) v = &emcell::cell_variants[emcell::cell_variants_count - 1];
+  r = v->r;
+  uint32_t tcap = c->cell_p995 > 32u * r ? ((c->cell_p995 - 32u * r + 31u) & ~31u) : 0u;
+  tcap = std::max<uint32_t>(tcap, 32);  // room for the odd pair beyond the sampled percentile
+  if (const char *e = getenv("NGSLD_CELL_TCAP")) tcap = ((uint32_t)atoi(e) + 31u) & ~31u;
+  // at least two CTAs per SM: shrink the tail if it does not fit (pairs beyond it go to the dense kernel)
+  while (tcap > 0 && 2 * (emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap) + 1024) > (size_t)c->smem_optin) tcap -= 32;
+  const size_t smem = emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap);
+  if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
+  int occ = 0;
+  for (const void *fn : {v->fn, v->fn_fused}) {
+    CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, emcell::CTA_THREADS, smem));
+  }
+  if (occ < 1) return NGSLD_OK;
+  ch.cell = v;
+  ch.cell_tcap = tcap;
+  ch.cell_smem = smem;
+  ch.blocks_cell = occ * c->sm_count;
+  ch.cell_fuse = true;
+  if (const char *e = getenv("NGSLD_CELL_FUSE")) ch.cell_fuse = atoi(e) != 0;
+  // the dense kernel for the left-over pairs, whatever the sample size
+  return choose_warp(c, ch, 1, true);
+}
+
 int choose_em(ngsld_ctx *c, const Plan &pl, EmChoice &ch) {
-  int rcw = choose_warp(c, ch, 3);
+  int rcw = choose_cell(c, ch);
+  if (rcw) return rcw;
+  if (ch.cell && ch.w) return NGSLD_OK;
+  ch.cell = nullptr;
+  rcw = choose_warp(c, ch, 3);
   if (rcw) return rcw;
   ch.v = pick_variant(c->n_ind);
   if (!ch.v) {
@@ -563,17 +653,21 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   c->stats.n_launches += 2;
   CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, NGSLD_WORK_COUNTERS * sizeof(unsigned long long), c->s_main));
   CUDA_TRY(c, cudaEventRecord(b.ev_ready, c->s_main));
+  const bool use_cell = ch.cell != nullptr && ch.w != nullptr && !P.strict;
+  const bool fused = use_cell && ch.cell_fuse;
   // r2_ExpG on the auxiliary stream, launched BEFORE the EM so that its CTAs are resident beside the EM's
+  // (not needed when the cell kernel computes it itself)
   CUDA_TRY(c, cudaStreamWaitEvent(c->s_aux, b.ev_ready, 0));
   CUDA_TRY(c, cudaEventRecord(b.ev_p0, c->s_aux));
-  {
+  if (!fused) {
     const bool beside_em = ch.w != nullptr && !P.strict;
     // four warps per SM: with fewer, the r2_ExpG kernel (which only gets the issue slots the EM leaves) becomes the
     // critical path (measured: 96 threads -> 22 M pairs/s, 64 -> 15.5 M, against 27 M)
-    int pth = 128;
+    int pth = 128, pctas = 1;
     if (const char *e = getenv("NGSLD_PEARSON_THREADS")) pth = std::max(32, std::min(128, atoi(e) / 32 * 32));
+    if (const char *e = getenv("NGSLD_PEARSON_CTAS")) pctas = std::max(1, std::min(16, atoi(e)));
     const unsigned long long want = (n + pth - 1) / pth;
-    const unsigned pb = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * (beside_em ? 1 : 16));
+    const unsigned pb = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * (beside_em ? pctas : 16));
     aux::pearson_kernel<<<pb, pth, 0, c->s_aux>>>(T, C, c->d_ctr);
     c->stats.n_launches++;
   }
@@ -581,6 +675,8 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   // EM
   if (P.strict || (ch.v == nullptr && ch.w == nullptr))
     snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "aux::em_strict_kernel");
+  else if (use_cell)
+    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emcell::em_cell_kernel<R=%d,FUSE=%d>", ch.cell->r, fused ? 1 : 0);
   else if (ch.w)
     snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emwarp::em_warp_kernel<R=%d,G=%d>", ch.w->r, ch.w->g);
   else
@@ -590,6 +686,9 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   if (P.strict || (ch.v == nullptr && ch.w == nullptr)) {
     const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
     aux::em_strict_kernel<<<sb, 128, 0, c->s_main>>>(T, C, P.ignore_miss_data, c->d_ctr);
+  } else if (use_cell) {
+    int rcc = launch_cell(c, ch, T, C, P.ignore_miss_data, b.d_resid);
+    if (rcc) return rcc;
   } else if (ch.w) {
     int rcw = launch_warp(c, ch, T, C, P.ignore_miss_data);
     if (rcw) return rcw;
@@ -809,6 +908,10 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   DevCounters hc;
   CUDA_TRY(c, cudaMemcpy(&hc, c->d_ctr, sizeof hc, cudaMemcpyDeviceToHost));
   c->stats.sum_em_passes = hc.em_passes;
+  c->stats.sum_cells = hc.cells;
+  c->stats.sum_cell_passes = hc.cell_passes;
+  c->stats.n_cell_pairs = hc.cell_pairs;
+  c->stats.n_resid_pairs = hc.resid_pairs;
   return NGSLD_OK;
 }
 
@@ -885,6 +988,11 @@ void ngsld_destroy(ngsld_ctx *c) {
   dfree(c->d_q);
   dfree(c->d_dx_sig);
   dfree(c->d_dx_se);
+  dfree(c->d_cls);
+  dfree(c->d_pal);
+  dfree(c->d_pal_k);
+  dfree(c->d_pal_miss);
+  dfree(c->d_cell_stats);
   dfree(c->d_cum);
   dfree(c->d_seg);
   dfree(c->d_label_blob);
@@ -955,6 +1063,7 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
   dfree(c->d_label_off);
   c->have_pos = c->have_labels = false;
   const uint64_t n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
+  const uint64_t n_cpad = (n_ind + 15) & ~15ull;  // class rows (one byte per individual) are read as 32-bit words
   const size_t row_bytes = n_pad * 24;
   if (n_sites != c->n_sites || n_ind != c->n_ind || !c->d_gl) {  // same shape as last time: keep the device buffers
     dfree(c->d_gl);
@@ -965,6 +1074,10 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     dfree(c->d_seg);
     dfree(c->d_expg);
     dfree(c->d_ratio);
+    dfree(c->d_cls);
+    dfree(c->d_pal);
+    dfree(c->d_pal_k);
+    dfree(c->d_pal_miss);
     c->n_sites = c->n_ind = 0;
     CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
     CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
@@ -974,15 +1087,62 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&c->d_expg, n_sites * n_ind * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_pad * sizeof(uint64_t)));
+    if (n_ind < 65536) {  // joint-class counters are 16 bits wide
+      CUDA_TRY(c, cudaMalloc(&c->d_cls, n_sites * n_cpad));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal, n_sites * (size_t)NGSLD_KMAX * 3 * sizeof(double)));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal_k, n_sites));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal_miss, n_sites * sizeof(uint64_t)));
+    }
+    if (!c->d_cell_stats) CUDA_TRY(c, cudaMalloc(&c->d_cell_stats, 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int)));
   }
   c->n_sites = n_sites;
   c->n_ind = n_ind;
   c->n_pad = n_pad;
+  c->n_cpad = n_cpad;
   CUDA_TRY(c, cudaMemsetAsync(c->d_seg, 0, n_sites * sizeof(uint32_t), c->s_main));
   if (n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * row_bytes, c->s_main));
   CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, row_bytes, gl, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
   CUDA_TRY(c, cudaMemcpyAsync(c->d_maf, maf, n_sites * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
   c->h_maf.assign(maf, maf + n_sites);
+  // site palettes for the class-compressed EM, and a sample of pairs to see whether it pays on this data
+  c->cell_ok = c->cell_possible = false;
+  c->cell_mean = c->cell_uncoded_frac = 0;
+  c->cell_p995 = 0;
+  if (c->d_cls && n_sites >= 2) {
+    const unsigned pblocks = (unsigned)std::min<uint64_t>((n_sites + 3) / 4, (uint64_t)c->sm_count * 16);
+    emcell::build_palette_kernel<<<pblocks, emcell::CTA_THREADS, 0, c->s_main>>>(
+        c->d_gl, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad, (uint32_t)n_cpad, c->d_cls, c->d_pal, c->d_pal_k, c->d_pal_miss);
+    const size_t stat_bytes = 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int);
+    CUDA_TRY(c, cudaMemsetAsync(c->d_cell_stats, 0, stat_bytes, c->s_main));
+    const uint32_t n_samples = 4096;
+    SiteTable T = site_table(c);
+    emcell::cell_stats_kernel<<<c->sm_count * 2, emcell::CTA_THREADS, 0, c->s_main>>>(
+        T, n_samples, 0, c->d_cell_stats, reinterpret_cast<unsigned int *>(c->d_cell_stats + 3));
+    CUDA_TRY(c, cudaGetLastError());
+    struct {
+      unsigned long long sum, n, uncoded;
+      unsigned int hist[132];
+    } hs;
+    static_assert(sizeof(hs) == 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int), "layout");
+    CUDA_TRY(c, cudaMemcpyAsync(&hs, c->d_cell_stats, stat_bytes, cudaMemcpyDeviceToHost, c->s_main));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+    const unsigned long long coded = hs.n - hs.uncoded;
+    c->cell_uncoded_frac = hs.n ? (double)hs.uncoded / (double)hs.n : 1.0;
+    if (coded) {
+      c->cell_mean = (double)hs.sum / (double)coded;
+      unsigned long long acc = 0;
+      uint32_t b = 0;
+      for (; b < 129; b++) {
+        acc += hs.hist[b];
+        if ((double)acc >= 0.995 * (double)coded) break;
+      }
+      c->cell_p995 = 32u * (std::min<uint32_t>(b, 128) + 1);
+      c->cell_possible = true;
+      // pays when a pair has clearly fewer cells than individuals and (almost) every site could be coded; below 160
+      // individuals the sub-warp group kernels are the better fit
+      c->cell_ok = n_ind >= 160 && c->cell_uncoded_frac <= 0.05 && c->cell_mean <= 0.7 * (double)n_ind;
+    }
+  }
   // per-site x87 terms of the expected-genotype correlation
   const char *host_terms = getenv("NGSLD_HOST_TERMS");
   if (host_terms && atoi(host_terms)) {
@@ -1344,9 +1504,13 @@ int ngsld_pairs(ngsld_ctx *c, const uint32_t *s1, const uint32_t *s2, uint64_t n
     aux::fill_rows_kernel<<<gb, 256, 0, c->s_main>>>(T, C);
     const unsigned pb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
     CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, NGSLD_WORK_COUNTERS * sizeof(unsigned long long), c->s_main));
-    aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C, c->d_ctr);
+    const bool use_cell = ch.cell && ch.w && !strict;
+    if (!(use_cell && ch.cell_fuse)) aux::pearson_kernel<<<pb, 128, 0, c->s_main>>>(T, C, c->d_ctr);
     if (strict || (!ch.v && !ch.w)) {
       aux::em_strict_kernel<<<pb, 128, 0, c->s_main>>>(T, C, ignore_miss_data, c->d_ctr);
+    } else if (use_cell) {
+      int rcc = launch_cell(c, ch, T, C, ignore_miss_data, b.d_resid);
+      if (rcc) return rcc;
     } else if (ch.w) {
       int rcw = launch_warp(c, ch, T, C, ignore_miss_data);
       if (rcw) return rcw;

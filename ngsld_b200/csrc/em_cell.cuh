@@ -1,0 +1,288 @@
+// Class-compressed fast EM (replaces haplo_freq + pair_freq_iter, reference shared/gen_func.cpp:1027-1119).
+//
+// The reference's E-step treats every individual separately, but its contribution to a pass depends only on the
+// individual's two genotype-likelihood triples (p at site 1, q at site 2).  Sequencing data at low depth has few
+// DISTINCT triples per site -- a triple is a function of the reads an individual happens to have (no reads: flat;
+// one read: two possibilities; called genotypes: three or four values in total) -- so the n_ind terms of
+//     ff[k] += tmp_k / sum                                   (gen_func.cpp:1094-1104)
+// collapse into one term per distinct (p, q) combination, weighted by the number of individuals that have it:
+//     a_k = sum over cells c of  w_c * i_k(p_c, q_c) / s(p_c, q_c)
+// This is the same fixed-point iteration as em_warp.cuh with the sum over individuals regrouped (equal terms added
+// w times become one product), so results agree with the bit-faithful kernel to ~1e-15 at equal nIter, and the cost
+// of a pass falls from n_ind E-steps to n_cells (BASELINE config 3, 500 individuals at 2x depth: ~160 cells).  With
+// called genotypes (reference call_geno, gen_func.cpp:886-914) a pair has at most 16 cells whatever the sample size.
+//
+// Per site, build_palette_kernel lists the distinct triples (the "palette", at most NGSLD_KMAX entries, bitwise
+// equality) and codes every individual as one byte.  Per pair, a warp
+//   1. counts the joint classes (c1[i], c2[i]) of the individuals in a 64 x 64 table of 16-bit counters in shared
+//      memory (lanes with equal keys are combined with match.any, so no two lanes touch the same counter), noting every
+//      counter that becomes non-zero in a list: the pair's cells;
+//   2. loads the cells -- palette triples + weight -- into registers (R per lane; cells beyond 32 R go to a shared-
+//      memory tail) and zeroes the counters it used;
+//   3. iterates the EM exactly like em_warp.cuh, one weighted E-step per cell.
+// Pairs it cannot take (a site with more than NGSLD_KMAX distinct triples, more cells than the warp has room for) are
+// appended to a list that the dense warp-per-pair kernel processes right afterwards.
+//
+// r2_ExpG (pearson.cuh) is order-dependent 80-bit arithmetic and cannot be regrouped; with FUSE it runs inside this
+// kernel -- every warp first does the 32 pairs of its batch one pair per lane, then their EMs one after the other -- so
+// the integer-only emulation and the FP64-bound EM share every SM without a second kernel to balance against.
+#pragma once
+#include "common.cuh"
+#include "em_fast.cuh"
+#include "pearson.cuh"
+
+namespace emcell {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
+constexpr int NBINS = NGSLD_KMAX * NGSLD_KMAX;
+
+using emfast::Ind;
+using emfast::estep;
+
+struct CellArgs {
+  uint32_t *resid;    // [chunk rows] indices (inside the chunk) of the pairs left to the dense kernel
+  uint32_t tcap;      // cells a warp can hold in shared memory beyond its 32 R register cells (multiple of 32)
+  int ignore_miss;    // --ignore_miss_data: individuals whose class is flat at either site are left out
+  int fuse_pearson;   // compute r2_ExpG in this kernel
+};
+
+// shared memory of one warp: joint-class counters | cell keys | tail cells (7 doubles each, structure of arrays)
+__host__ __device__ inline size_t warp_smem_bytes(int r, uint32_t tcap) {
+  const size_t keys = ((size_t)(32 * r + tcap) * 2 + 15) & ~(size_t)15;
+  return (size_t)NBINS * 2 + keys + (size_t)tcap * 7 * 8;
+}
+
+__device__ __forceinline__ void wipe_bins(uint16_t *bins, int lane) {
+  uint4 *b = reinterpret_cast<uint4 *>(bins);
+  for (int k = lane; k < NBINS * 2 / 16; k += 32) b[k] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+}
+
+// Joint classes of a pair.  bins must be all zero on entry; on return bins[key] = individuals with joint class key
+// (key = c1 * 64 + c2), keys[0 .. min(n_cells, cap)) = the distinct keys in order of first appearance, n_used =
+// individuals counted.  Returns n_cells (if it exceeds cap the caller has to wipe the whole table).
+__device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s1, uint32_t s2, bool ign, uint16_t *bins,
+                                                  uint16_t *keys, uint32_t cap, uint32_t &n_used, int lane) {
+  const uint8_t *c1 = T.cls + (size_t)s1 * T.n_cpad, *c2 = T.cls + (size_t)s2 * T.n_cpad;
+  const uint64_t miss1 = ign ? T.pal_miss[s1] : 0ull, miss2 = ign ? T.pal_miss[s2] : 0ull;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t n_cells = 0, used = 0;
+  for (uint32_t blk = 0; blk < T.n_ind; blk += 128u) {
+    const uint32_t i0 = blk + 4u * (uint32_t)lane;  // this lane's four individuals of the block
+    uint32_t w1 = 0, w2 = 0;
+    if (i0 < T.n_ind) {
+      w1 = *reinterpret_cast<const uint32_t *>(c1 + i0);
+      w2 = *reinterpret_cast<const uint32_t *>(c2 + i0);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const uint32_t a = (w1 >> (8 * e)) & 255u, b = (w2 >> (8 * e)) & 255u;
+      bool valid = i0 + e < T.n_ind;
+      if (valid && ign) valid = !((((miss1 >> a) | (miss2 >> b)) & 1ull) != 0);
+      const uint32_t key = valid ? (a << 6 | b) : 0xffffu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      const bool lead = valid && (__ffs(peers) - 1 == lane);
+      bool fresh = false;
+      if (lead) {
+        const uint32_t old = bins[key];
+        bins[key] = (uint16_t)(old + __popc(peers));
+        fresh = old == 0;
+      }
+      const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
+      if (fresh) {
+        const uint32_t slot = n_cells + __popc(fm & lt);
+        if (slot < cap) keys[slot] = (uint16_t)key;
+      }
+      n_cells += __popc(fm);
+      used += __popc(__ballot_sync(0xffffffffu, valid));
+      __syncwarp();  // the counters written here are read by whichever lane leads the key next time
+    }
+  }
+  n_used = used;
+  return n_cells;
+}
+
+struct Cell {
+  Ind g;
+  double w;
+};
+
+__device__ __forceinline__ void cell_default(Cell &c) {  // an empty slot: weight 0, likelihoods that keep s finite
+  c.g.p0 = c.g.p1 = c.g.p2 = c.g.q0 = c.g.q1 = c.g.q2 = 1.0;
+  c.w = 0.0;
+}
+
+__device__ __forceinline__ void cell_load(Cell &c, const SiteTable &T, uint32_t s1, uint32_t s2, uint32_t key, uint16_t *bins) {
+  const double *pa = T.pal + ((size_t)s1 * NGSLD_KMAX + (key >> 6)) * 3;
+  const double *pb = T.pal + ((size_t)s2 * NGSLD_KMAX + (key & 63u)) * 3;
+  c.g.p0 = __ldg(pa); c.g.p1 = __ldg(pa + 1); c.g.p2 = __ldg(pa + 2);
+  c.g.q0 = __ldg(pb); c.g.q1 = __ldg(pb + 1); c.g.q2 = __ldg(pb + 2);
+  c.w = (double)bins[key];
+  bins[key] = 0;  // every counter in use belongs to exactly one cell: the table is clean again after the loads
+}
+
+__device__ __forceinline__ void cell_step(const double f0, const double f1, const double f2, const double f3, const Cell &c,
+                                          double &a0, double &a1, double &a2, double &a3) {
+  double i0, i1, i2, i3, s;
+  estep(f0, f1, f2, f3, c.g, i0, i1, i2, i3, s);
+  const double wi = c.w * emfast::rcp_fast(s);
+  a0 = __fma_rn(i0, wi, a0);
+  a1 = __fma_rn(i1, wi, a1);
+  a2 = __fma_rn(i2, wi, a2);
+  a3 = __fma_rn(i3, wi, a3);
+}
+
+// R  cells per lane held in registers (cell slot lane + 32 r); a pair may have up to 32 R + A.tcap cells.
+// Three CTAs of four warps per SM: 168 registers per thread.
+template <int R, bool FUSE>
+__global__ void __launch_bounds__(CTA_THREADS, 3) em_cell_kernel(SiteTable T, PairChunk C, CellArgs A, DevCounters *ctr) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t cap = 32u * R + A.tcap;
+  unsigned char *mine = dyn_smem + (size_t)warp * warp_smem_bytes(R, A.tcap);
+  uint16_t *bins = reinterpret_cast<uint16_t *>(mine);
+  uint16_t *keys = bins + NBINS;
+  double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap) - (size_t)A.tcap * 56);
+  wipe_bins(bins, lane);
+  const bool ign = A.ignore_miss != 0;
+  unsigned long long my_passes = 0, my_cell_passes = 0, my_cells = 0, my_pairs = 0, my_resid = 0;
+
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->next_pair, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= C.n_pairs) break;
+    const unsigned long long me = base + lane;
+    const bool have = me < C.n_pairs;
+    uint32_t my_s1 = 0, my_s2 = 0;
+    if (have) {
+      my_s1 = C.s1[me];
+      my_s2 = C.s2[me];
+    }
+    // ---- r2_ExpG of the batch, one pair per lane ----
+    if (FUSE && have) C.rows[me].r2_expg = pearson::pair_r2(T, my_s1, my_s2);
+    __syncwarp();
+    const int nb = C.n_pairs - base < 32ull ? (int)(C.n_pairs - base) : 32;
+
+    // ---- the batch's EMs, the whole warp on one pair at a time ----
+    for (int j = 0; j < nb; j++) {
+      const uint32_t s1 = __shfl_sync(0xffffffffu, my_s1, j), s2 = __shfl_sync(0xffffffffu, my_s2, j);
+      const unsigned long long idx = base + j;
+      const uint32_t k1 = T.pal_k[s1], k2 = T.pal_k[s2];
+      uint32_t n_cells = 0, n_used = T.n_ind;
+      bool mine_ok = k1 != 0 && k2 != 0;
+      if (mine_ok) {
+        n_cells = joint_classes(T, s1, s2, ign, bins, keys, cap, n_used, lane);
+        if (n_cells > cap) {
+          wipe_bins(bins, lane);
+          mine_ok = false;
+        }
+      }
+      if (!mine_ok) {  // left to the dense kernel
+        if (lane == 0) A.resid[atomicAdd(&ctr->n_resid, 1ull)] = (uint32_t)idx;
+        my_resid++;
+        continue;
+      }
+      // ---- cells -> registers (slot lane + 32 r) and the shared-memory tail (slots 32 R ...) ----
+      Cell g[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const uint32_t slot = (uint32_t)lane + 32u * r;
+        cell_default(g[r]);
+        if (slot < n_cells) cell_load(g[r], T, s1, s2, keys[slot], bins);
+      }
+      const uint32_t n_tail = n_cells > 32u * R ? n_cells - 32u * R : 0u;
+      const uint32_t n_tail_pad = (n_tail + 31u) & ~31u;  // whole warps: the last one is filled up with empty cells
+      for (uint32_t t = lane; t < n_tail_pad; t += 32u) {
+        Cell c;
+        cell_default(c);
+        if (t < n_tail) cell_load(c, T, s1, s2, keys[32u * R + t], bins);
+        tail[0 * A.tcap + t] = c.g.p0; tail[1 * A.tcap + t] = c.g.p1; tail[2 * A.tcap + t] = c.g.p2;
+        tail[3 * A.tcap + t] = c.g.q0; tail[4 * A.tcap + t] = c.g.q1; tail[5 * A.tcap + t] = c.g.q2;
+        tail[6 * A.tcap + t] = c.w;
+      }
+      __syncwarp();
+
+      const double inv_x = __ddiv_rn(1.0, (double)n_used);
+      const double m1 = T.maf[s1], m2 = T.maf[s2];  // haplo_freq start point, gen_func.cpp:1034-1037
+      double f0 = __dmul_rn(__dsub_rn(1.0, m1), __dsub_rn(1.0, m2));
+      double f1 = __dmul_rn(__dsub_rn(1.0, m1), m2);
+      double f2 = __dmul_rn(m1, __dsub_rn(1.0, m2));
+      double f3 = __dmul_rn(m1, m2);
+      double A0 = 0, A1 = 0, A2 = 0, A3 = 0;
+      uint32_t it = 0;
+      bool conv = false;
+      for (;;) {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (32u * r < n_cells) cell_step(f0, f1, f2, f3, g[r], a0, a1, a2, a3);  // warp-uniform: skips empty levels
+        for (uint32_t t = lane; t < n_tail_pad; t += 32u) {
+          Cell c;
+          c.g.p0 = tail[0 * A.tcap + t]; c.g.p1 = tail[1 * A.tcap + t]; c.g.p2 = tail[2 * A.tcap + t];
+          c.g.q0 = tail[3 * A.tcap + t]; c.g.q1 = tail[4 * A.tcap + t]; c.g.q2 = tail[5 * A.tcap + t];
+          c.w = tail[6 * A.tcap + t];
+          cell_step(f0, f1, f2, f3, c, a0, a1, a2, a3);
+        }
+        emfast::group_sum4<32>(a0, a1, a2, a3, lane);
+        // ---- M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5) ----
+        A0 = f0 * a0; A1 = f1 * a1; A2 = f2 * a2; A3 = f3 * a3;
+        const double n0 = A0 * inv_x, n1 = A1 * inv_x, n2 = A2 * inv_x, n3 = A3 * inv_x;
+        // eps starts at 0 and a NaN difference never raises it (the reference's `if (d > eps)` chain)
+        double eps = fmax(0.0, fabs(n0 - f0));
+        eps = fmax(eps, fabs(n1 - f1));
+        eps = fmax(eps, fabs(n2 - f2));
+        eps = fmax(eps, fabs(n3 - f3));
+        f0 = n0; f1 = n1; f2 = n2; f3 = n3;
+        conv = eps < NGSLD_EPS;
+        if (conv || it == NGSLD_ITER_MAX - 1) break;
+        it++;
+      }
+      if (lane == 0) {
+        // Output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113): true divisions and the
+        // sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes.
+        const double xd = (double)n_used;
+        double gq[4] = {__ddiv_rn(A0, xd), __ddiv_rn(A1, xd), __ddiv_rn(A2, xd), __ddiv_rn(A3, xd)};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));
+        derive_and_store(C.rows + idx, gq, conv ? it : (uint32_t)NGSLD_ITER_MAX, n_used);
+      }
+      my_passes += it + 1;
+      my_cell_passes += (unsigned long long)(it + 1) * n_cells;
+      my_cells += n_cells;
+      my_pairs++;
+      __syncwarp();  // every lane is done with the tail before the next pair overwrites it
+    }
+  }
+  if (lane == 0) {
+    if (my_passes) atomicAdd(&ctr->em_passes, my_passes);
+    if (my_cell_passes) atomicAdd(&ctr->cell_passes, my_cell_passes);
+    if (my_cells) atomicAdd(&ctr->cells, my_cells);
+    if (my_pairs) atomicAdd(&ctr->cell_pairs, my_pairs);
+    if (my_resid) atomicAdd(&ctr->resid_pairs, my_resid);
+  }
+}
+
+// ---- per-site palettes ------------------------------------------------------------------------------------------
+// One warp per site: the distinct triples of the site's row in order of first appearance (bitwise equality), the class
+// of every individual, and which classes are "missing data".  A site with more than NGSLD_KMAX distinct triples gets
+// pal_k = 0 and is not coded.
+__global__ void __launch_bounds__(CTA_THREADS) build_palette_kernel(const double *gl, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad, uint32_t n_cpad,
+                                     uint8_t *cls, double *pal, uint8_t *pal_k, uint64_t *pal_miss);
+
+// n_samples pseudo-random pairs: out[0] = sum of cells, out[1] = pairs sampled, out[2] = pairs with an uncoded site,
+// hist[b] = pairs with 32 b <= cells < 32 (b + 1) (129 buckets).  Decides whether (and with which tail capacity) the cell
+// kernel is used for this data set.
+__global__ void __launch_bounds__(CTA_THREADS) cell_stats_kernel(SiteTable T, uint32_t n_samples, int ignore_miss, unsigned long long *out,
+                                  unsigned int *hist);
+
+struct CellVariant {
+  int r;
+  const void *fn, *fn_fused;
+};
+extern const CellVariant cell_variants[];
+extern const int cell_variants_count;
+
+}  // namespace emcell

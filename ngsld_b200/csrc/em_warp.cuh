@@ -95,8 +95,11 @@ struct TailVec {
 //      footprint of a 500-individual pair for samples of 1000 (G = 2) or 2000 (G = 4) individuals.
 // Register cap: 152 (R >= 5) keeps three CTAs (58 K registers) plus one CTA of the r2_ExpG kernel (5 K) resident per SM;
 // 128 (R <= 4) allows four CTAs.
+// sel / n_sel: when sel is not NULL the kernel works through the pairs sel[0 .. *n_sel) (indices into the chunk) instead of
+//      all of them: the pairs the class-compressed kernel (em_cell.cuh) left over, counted on the device.
 template <int R, bool IGN, int U, int G>
-__global__ void __maxnreg__(R <= 4 ? 128 : 152) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr) {
+__global__ void __maxnreg__(R <= 4 ? 128 : 152) em_warp_kernel(SiteTable T, PairChunk C, DevCounters *ctr, const uint32_t *sel,
+                                                               const unsigned long long *n_sel) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t bars[WARPS_PER_CTA];
   __shared__ double red[WARPS_PER_CTA / G][2][G][4];            // per group, double-buffered by pass parity
@@ -127,18 +130,21 @@ __global__ void __maxnreg__(R <= 4 ? 128 : 152) em_warp_kernel(SiteTable T, Pair
   const uint32_t sa = emfast::smem_u32(dyn_smem) + (uint32_t)warp * 2u * slot_bytes + (uint32_t)lane * 48u;
   const uint32_t sb = sa + slot_bytes;
 
+  const unsigned long long n_work = sel ? *n_sel : C.n_pairs;
+  unsigned long long *next = sel ? &ctr->next_resid : &ctr->next_pair;
   for (;;) {
     unsigned long long idx = 0;
     if (G == 1) {
-      if (lane == 0) idx = atomicAdd(&ctr->next_pair, 1ull);
+      if (lane == 0) idx = atomicAdd(next, 1ull);
       idx = __shfl_sync(0xffffffffu, idx, 0);
     } else {
       // the last reduction barrier of the previous pair orders every read of fetched[] before this write
-      if (gw == 0 && lane == 0) fetched[grp] = atomicAdd(&ctr->next_pair, 1ull);
+      if (gw == 0 && lane == 0) fetched[grp] = atomicAdd(next, 1ull);
       emfast::named_bar_sync(1 + grp, 32 * G);
       idx = fetched[grp];
     }
-    if (idx >= C.n_pairs) break;
+    if (idx >= n_work) break;
+    if (sel) idx = sel[idx];
     const uint32_t s1 = C.s1[idx], s2 = C.s2[idx];
     const double *row_a = T.gl + ((size_t)s1 * T.n_pad + lo) * 3, *row_b = T.gl + ((size_t)s2 * T.n_pad + lo) * 3;
 

@@ -41,7 +41,7 @@ def test_no_torch_or_cpp_types_in_the_abi():
 
 
 def test_abi_version_and_row_layout():
-    assert N.load_library().ngsld_abi_version() == 1
+    assert N.load_library().ngsld_abi_version() == 2
     assert N.ROW_DTYPE.itemsize == 112
 
 

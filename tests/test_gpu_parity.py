@@ -93,10 +93,12 @@ def test_rows_strict_bit_exact_and_fast_within_tolerance(G, fx, variant, tmp_pat
     assert np.array_equal(fast["dist"], strict["dist"])
 
 
-# every (individuals-per-lane, lanes-per-group) kernel instantiation family, incl. ragged tails
+# every (individuals-per-lane, lanes-per-group) kernel instantiation family, incl. ragged tails; for each sample size
+# the default kernel family, the class-compressed kernel forced (NGSLD_EM_PATH=cell) and, from 160 individuals, the
+# dense warp-per-pair kernel forced (NGSLD_EM_PATH=warp)
 @pytest.mark.parametrize("n_ind", [1, 2, 3, 7, 24, 32, 33, 64, 65, 100, 128, 129, 159, 160, 250, 256, 257, 500, 513, 1000, 1025, 2047, 2500, 5001])
 @pytest.mark.parametrize("ignore_miss", [False, True])
-def test_every_group_shape_against_oracle(G, n_ind, ignore_miss):
+def test_every_group_shape_against_oracle(G, n_ind, ignore_miss, monkeypatch):
     n_sites = 14 if n_ind <= 256 else 8
     GL, _ = H.gen_synth.synth(n_sites, n_ind, 1000 + n_ind)
     opt = H.parse_flags(["--max_kb_dist", "0"] + (["--ignore_miss_data"] if ignore_miss else []))
@@ -105,11 +107,18 @@ def test_every_group_shape_against_oracle(G, n_ind, ignore_miss):
     ref = G.oracle_rows(arrays, s1, s2, ignore_miss)
     with eng:
         G.assert_strict_equal(eng.pairs(s1, s2, ignore_miss, strict=True), ref)
-        G.assert_fast_close(eng.pairs(s1, s2, ignore_miss, strict=False), ref)
-        p = G.scan_params(opt, False)
-        rows = eng.scan(p)            # window path (tile kernel where it applies)
-        assert np.array_equal(rows["s1"], s1) and np.array_equal(rows["s2"], s2)
-        G.assert_fast_close(rows, ref)
+        for path in [None, "cell"] + (["warp"] if n_ind >= 160 else []):
+            if path:
+                monkeypatch.setenv("NGSLD_EM_PATH", path)
+            G.assert_fast_close(eng.pairs(s1, s2, ignore_miss, strict=False), ref)
+            p = G.scan_params(opt, False)
+            rows = eng.scan(p)            # window path
+            kernel = eng.stats()["em_kernel"]
+            assert np.array_equal(rows["s1"], s1) and np.array_equal(rows["s2"], s2)
+            G.assert_fast_close(rows, ref)
+            if path:
+                assert kernel.startswith("em" + path + "::"), kernel
+            monkeypatch.delenv("NGSLD_EM_PATH", raising=False)
 
 
 @pytest.mark.parametrize("path", ["list", "tile"])

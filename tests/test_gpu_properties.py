@@ -6,6 +6,8 @@
   * invariants of the domain: haplotype frequencies sum to 1, |D'| <= 1, 0 <= r2 <= 1, swapping the two sites of a
     pair swaps hap01/hap10 and leaves D, r2, r2_ExpG unchanged
   * every EM kernel family gives the same answer on the same pairs (warp-per-pair with 1/2/4 warps, group kernels)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -32,14 +34,19 @@ def big(G):
     eng.close()
 
 
-def test_large_scan_fast_vs_strict_sample_and_pass_checksum(G, big):
+@pytest.mark.parametrize("path", ["cell", "warp"])
+def test_large_scan_fast_vs_strict_sample_and_pass_checksum(G, big, path, monkeypatch):
     eng, arrays = big
+    monkeypatch.setenv("NGSLD_EM_PATH", path)
     P = N.ScanParams.make(max_kb_dist=0)
-    rows = eng.scan(P)                                   # 4.5 M pairs through the warp-per-pair kernel
+    rows = eng.scan(P)                                   # 4.5 M pairs
     st = eng.stats()
-    assert len(rows) == 3000 * 2999 // 2 and st["em_kernel"].startswith("emwarp::")
+    assert len(rows) == 3000 * 2999 // 2 and st["em_kernel"].startswith("em" + path + "::")
     it = rows["n_iter"].astype(np.int64)
     assert int(np.where(it < 100, it + 1, 100).sum()) == st["sum_em_passes"]
+    if path == "cell":   # 500 individuals at 2x depth: a pair has ~160 distinct (p, q) combinations, none is left over
+        assert st["n_cell_pairs"] + st["n_resid_pairs"] == len(rows) and st["n_resid_pairs"] <= len(rows) // 100
+        assert 100 < st["sum_cells"] / st["n_cell_pairs"] < 250
     sel = np.sort(np.random.default_rng(5).choice(len(rows), 20000, replace=False))
     strict = eng.pairs(rows["s1"][sel], rows["s2"][sel], strict=True)
     G.assert_fast_close(rows[sel], strict)
@@ -91,10 +98,20 @@ def G_same(a, b, tol):
     return bool(np.all(np.abs(a[fin] - b[fin]) <= tol)) and bool(np.all(np.isnan(a) == np.isnan(b)))
 
 
-@pytest.mark.parametrize("n_ind,env", [(500, {"NGSLD_WARP_R": "4"}), (500, {"NGSLD_WARP_G": "2"}), (500, {"NGSLD_WARP_G": "4"}),
+W = {"NGSLD_EM_PATH": "warp"}
+CELL = {"NGSLD_EM_PATH": "cell"}
+
+
+@pytest.mark.parametrize("n_ind,env", [(500, dict(W, NGSLD_WARP_R="4")), (500, dict(W, NGSLD_WARP_G="2")), (500, dict(W, NGSLD_WARP_G="4")),
                                        (500, {"NGSLD_EM_PATH": "tile"}), (500, {"NGSLD_EM_PATH": "list"}),
-                                       (1000, {}), (1000, {"NGSLD_EM_PATH": "list"}), (250, {"NGSLD_EM_PATH": "warp", "NGSLD_WARP_R": "3"}),
-                                       (90, {"NGSLD_EM_PATH": "warp"})])
+                                       (1000, W), (1000, {"NGSLD_EM_PATH": "list"}), (250, dict(W, NGSLD_WARP_R="3")),
+                                       (90, W),
+                                       # class-compressed kernel: default shape, r2_ExpG in a kernel of its own, cells mostly
+                                       # in the shared-memory tail, hardly any room (most pairs go to the dense kernel)
+                                       (500, CELL), (500, dict(CELL, NGSLD_CELL_FUSE="0")),
+                                       (500, dict(CELL, NGSLD_CELL_R="2", NGSLD_CELL_TCAP="160")),
+                                       (500, dict(CELL, NGSLD_CELL_R="4", NGSLD_CELL_TCAP="32")),
+                                       (1000, CELL), (2000, CELL), (2000, dict(CELL, NGSLD_CELL_TCAP="64")), (90, CELL), (250, {})])
 def test_every_kernel_family_agrees_with_strict(G, n_ind, env, monkeypatch):
     GL, _ = H.gen_synth.synth_fast(160, n_ind, 1234 + n_ind)
     gl, expg, maf = N.prepare_sites(GL)
@@ -153,3 +170,56 @@ def test_decay_bins_equal_numpy_binning_of_the_rows(bin_size, n_bins, kw):
         tot = np.bincount(k[fin], weights=v[fin], minlength=n_bins)
         assert np.array_equal(bins["n"][:, j], cnt), f
         assert np.allclose(bins["sum"][:, j], tot, rtol=1e-9, atol=1e-12), f
+
+
+@pytest.mark.parametrize("flags,max_cells", [(["--call_geno"], 9), (["--call_geno", "--N_thresh", "0.4", "--call_thresh", "0.4"], 16)])
+def test_called_genotypes_run_on_a_count_table(G, flags, max_cells):
+    """--call_geno (reference gen_func.cpp:886-914) makes every likelihood triple one-hot (or flat below N_thresh): a
+    pair then has at most 3 x 3 (4 x 4) distinct combinations and the class-compressed EM iterates on that count table,
+    whatever the sample size.  Same nIter, 1e-9, as for any other input."""
+    GL, _ = H.gen_synth.synth(120, 500, 4242)
+    opt = H.parse_flags(["--max_kb_dist", "0"] + flags)
+    eng, arrays = G.engine_for(GL, opt)
+    with eng:
+        fast = eng.scan(G.scan_params(opt, False))
+        st = eng.stats()
+        strict = eng.scan(G.scan_params(opt, True))
+        ign = eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=1))
+        ign_strict = eng.scan(N.ScanParams.make(max_kb_dist=0, ignore_miss_data=1, strict=1))
+    assert st["em_kernel"].startswith("emcell::") and st["n_resid_pairs"] == 0
+    assert st["sum_cells"] <= max_cells * st["n_cell_pairs"]
+    G.assert_fast_close(fast, strict)
+    G.assert_fast_close(ign, ign_strict)
+    few = np.random.default_rng(2).choice(len(fast), 60, replace=False)
+    G.assert_strict_equal(strict[few], G.oracle_rows(arrays, strict["s1"][few], strict["s2"][few]))
+
+
+def test_uncompressible_data_keeps_the_dense_kernel():
+    """Continuous likelihoods (every triple distinct): the palettes overflow, ngsld_set_sites sees that the class-
+    compressed kernel cannot pay, and the dense warp-per-pair kernel runs (also when NGSLD_EM_PATH=cell asks for the
+    other one: there is no palette to run it on)."""
+    rng = np.random.default_rng(12)
+    GL = rng.dirichlet([0.8, 0.8, 0.8], (40, 300))
+    gl, expg, maf = N.prepare_sites(GL)
+    with N.Engine(0) as eng:
+        eng.set_sites(gl, expg, maf)
+        P = N.ScanParams.make(max_kb_dist=0)
+        a = eng.scan(P)
+        assert eng.stats()["em_kernel"].startswith("emwarp::")
+        strict = eng.scan(N.ScanParams.make(max_kb_dist=0, strict=1))
+        # a few coded sites among uncoded ones: pairs touching an uncoded site are handed on to the dense kernel
+        GL2 = GL.copy()
+        GL2[::3] = H.gen_synth.synth(14, 300, 5)[0]
+        gl2, expg2, maf2 = N.prepare_sites(GL2)
+        eng.set_sites(gl2, expg2, maf2)
+        os.environ["NGSLD_EM_PATH"] = "cell"
+        try:
+            b = eng.scan(P)
+            st = eng.stats()
+        finally:
+            del os.environ["NGSLD_EM_PATH"]
+        strict2 = eng.scan(N.ScanParams.make(max_kb_dist=0, strict=1))
+    assert st["em_kernel"].startswith("emcell::") and st["n_resid_pairs"] > 0 and st["n_cell_pairs"] == 14 * 13 // 2
+    import gpu_helpers
+    gpu_helpers.assert_fast_close(b, strict2)
+    gpu_helpers.assert_fast_close(a, strict)
