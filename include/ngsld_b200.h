@@ -130,7 +130,8 @@ void ngsld_free(void *p);
  * call_geno() pass (ngsLD.cpp:92-98), est_maf() (ngsLD.cpp:103-104, shared/gen_func.cpp:974-1009) and
  * the conv_space/expected-genotype loop (ngsLD.cpp:107-114).  raw = the file's doubles
  * [n_sites][n_ind][3]; outputs gl [n_sites][n_ind][3] (normal space), expg [n_sites][n_ind], maf
- * [n_sites].  from_log_cells = 1: `raw` already holds log-space cells (text input path). */
+ * [n_sites].  from_log_cells = 1: `raw` already holds log-space cells (text input path).  gl may be the same
+ * buffer as raw (every cell is read before it is written): one genotype matrix in host memory, as in the reference. */
 int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int log_scale, int from_log_cells,
                         int ignore_miss_data, int call_geno, double N_thresh, double call_thresh, int n_threads,
                         double *gl, double *expg, double *maf);
@@ -144,6 +145,12 @@ int ngsld_set_sites(ngsld_ctx *ctx, const double *gl, const double *expg, const 
 /* replaces params.pos_dist / params.labels (ngsLD.cpp:119-135).  pos_dist NULL = all +inf (no --pos);
  * labels NULL = "(null)" like the reference prints.  labels are only used by ngsld_scan_tsv. */
 int ngsld_set_positions(ngsld_ctx *ctx, const double *pos_dist, const char *const *labels);
+
+/* Multi-GPU start-up: give dst everything ngsld_set_sites + ngsld_set_positions put on src's GPU by device-to-device
+ * copies (NVLink / NVSwitch when the devices are peers) instead of another upload through the host: the reference's
+ * threads share one `params`; here one GPU receives it from the host and passes it on.  Both contexts must belong to
+ * the calling process; src must not be scanning meanwhile. */
+int ngsld_share_sites(ngsld_ctx *dst, const ngsld_ctx *src);
 
 /* ---- the scan: replaces the threadpool_add(calc_pair_LD) fan-out + threadpool_wait ------------ */
 void ngsld_scan_defaults(ngsld_scan_params *p);
@@ -166,6 +173,17 @@ int ngsld_scan_into(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_
 /* TSV bytes exactly as the reference's fprintf block (ngsLD.cpp:314-351), formatted on the device. */
 int ngsld_scan_tsv(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_text_sink sink,
                    void *user);
+/* The same text into ONE caller buffer, no intermediate copy: every device chunk is copied from HBM straight to
+ * buf + running offset (true DMA when buf comes from ngsld_alloc_host).  ngsld_tsv_row_bound() * rows is always enough
+ * room unless a value needs the host formatter (|x| >= 1e9); a scan that does not fit fails with NGSLD_E_INVALID. */
+int ngsld_scan_tsv_into(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, char *buf, uint64_t cap,
+                        uint64_t *n_bytes, uint64_t *n_rows);
+/* upper bound of the bytes of one TSV row the device formatter writes (depends on the longest label). */
+uint64_t ngsld_tsv_row_bound(const ngsld_ctx *ctx, int extend_out);
+/* page-locked host memory usable from every device (cudaHostAlloc, portable), for result buffers that the GPUs fill
+ * by DMA and a writer thread hands to write(2) as they are. */
+int ngsld_alloc_host(void **p, size_t bytes);
+void ngsld_free_host(void *p);
 /* Same work with results left in device memory (no D2H): the HBM-resident timing leg of bench.py. */
 int ngsld_scan_device(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p);
 int ngsld_get_stats(const ngsld_ctx *ctx, ngsld_scan_stats *out);

@@ -98,6 +98,11 @@ def load_library():
         "ngsld_scan_into": (i32, [vp, u64, u64, C.POINTER(ScanParams), vp, u64, C.POINTER(u64)]),
         "ngsld_scan_tsv": (i32, [vp, u64, u64, C.POINTER(ScanParams), TEXT_SINK, vp]),
         "ngsld_scan_device": (i32, [vp, u64, u64, C.POINTER(ScanParams)]),
+        "ngsld_scan_tsv_into": (i32, [vp, u64, u64, C.POINTER(ScanParams), vp, u64, C.POINTER(u64), C.POINTER(u64)]),
+        "ngsld_tsv_row_bound": (u64, [vp, i32]),
+        "ngsld_alloc_host": (i32, [C.POINTER(vp), C.c_size_t]),
+        "ngsld_free_host": (None, [vp]),
+        "ngsld_share_sites": (i32, [vp, vp]),
         "ngsld_get_stats": (i32, [vp, C.POINTER(ScanStats)]),
         "ngsld_scan_decay": (i32, [vp, u64, u64, C.POINTER(ScanParams), dbl, u64, vp, C.POINTER(u64)]),
         "ngsld_pairs": (i32, [vp, pu32, pu32, u64, i32, i32, vp]),
@@ -123,7 +128,8 @@ EXPORTED = ["ngsld_abi_version", "ngsld_device_count", "ngsld_create", "ngsld_de
             "ngsld_scan_defaults", "ngsld_scan_count", "ngsld_partition", "ngsld_scan", "ngsld_scan_into",
             "ngsld_scan_tsv", "ngsld_scan_device", "ngsld_get_stats", "ngsld_pairs", "ngsld_site_seeds",
             "ngsld_tsv_header", "ngsld_probe_fp64", "ngsld_plan_count", "ngsld_plan_partition", "ngsld_load_geno",
-            "ngsld_load_positions", "ngsld_free", "ngsld_scan_decay"]
+            "ngsld_load_positions", "ngsld_free", "ngsld_scan_decay", "ngsld_scan_tsv_into", "ngsld_tsv_row_bound",
+            "ngsld_alloc_host", "ngsld_free_host", "ngsld_share_sites"]
 
 
 def prepare_sites(raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,
@@ -332,6 +338,32 @@ class Engine:
             out.write(head)
         self._check(self._lib.ngsld_scan_tsv(self._h, s1_lo, hi, C.byref(params), cb, None))
         return None if out is not None else head + b"".join(chunks)
+
+    def scan_tsv_into(self, params, s1_lo=0, s1_hi=None, pinned=True):
+        """ngsld_scan_tsv_into: the scan's TSV text through one (page-locked) buffer sized with ngsld_tsv_row_bound."""
+        hi = self.n_sites if s1_hi is None else s1_hi
+        cap = max(1, self.count(params, s1_lo, hi)) * self._lib.ngsld_tsv_row_bound(self._h, params.extend_out)
+        buf = C.c_void_p()
+        if pinned:
+            rc = self._lib.ngsld_alloc_host(C.byref(buf), cap)
+            if rc != 0:
+                raise NgsldError(rc, _global_error())
+            ptr = buf
+        else:
+            keep = C.create_string_buffer(cap)
+            ptr = C.cast(keep, C.c_void_p)
+        try:
+            nb, nr = C.c_uint64(0), C.c_uint64(0)
+            self._check(self._lib.ngsld_scan_tsv_into(self._h, s1_lo, hi, C.byref(params), ptr, cap, C.byref(nb), C.byref(nr)))
+            return C.string_at(ptr, nb.value), nr.value
+        finally:
+            if pinned:
+                self._lib.ngsld_free_host(buf)
+
+    def share_sites_from(self, other):
+        """ngsld_share_sites: take over the site table of another Engine (another GPU) by device-to-device copy."""
+        self._check(self._lib.ngsld_share_sites(self._h, other._h))
+        self.n_sites, self.n_ind = other.n_sites, other.n_ind
 
     def scan_device(self, params, s1_lo=0, s1_hi=None):
         hi = self.n_sites if s1_hi is None else s1_hi

@@ -2,15 +2,19 @@
 //
 // Same flags, defaults, implications and validation messages as the reference CLI (parse_args.cpp:6-29,35-59,
 // 63-132,168-183), same header and TSV bytes on --out / stdout (ngsLD.cpp:77,314-351).  The thread-pool fan-out of
-// the reference's main (ngsLD.cpp:153-198) becomes: one ngsld context per GPU, the first-site axis split into
-// equal-pair-count slabs (ngsld_partition), one host thread per GPU taking slabs in order and running ngsld_scan_tsv,
-// and a writer thread appending the finished slabs in slab order — the row order the reference produces with
-// --n_threads 1 — while the GPUs work on the next ones.
+// the reference's main (ngsLD.cpp:153-198) becomes: one ngsld context per GPU (the site table is uploaded once and
+// passed on GPU to GPU), the first-site axis split into equal-pair-count slabs (ngsld_partition), one host thread per
+// GPU taking slabs in order and letting the device write each slab's text straight into a page-locked buffer
+// (ngsld_scan_tsv_into), and writer threads that pwrite() finished slabs at their final offsets -- the row order the
+// reference produces with --n_threads 1 -- while the GPUs work on the next ones.  The mutexed fprintf of
+// ngsLD.cpp:310-352 has no counterpart: text is produced on the device and copied once, by the kernel's write().
 //
 // Extra flags (distinct prefix, reference command lines stay valid):
 //   --gpu_n INT       GPUs to use (default: all visible)
 //   --gpu_strict      bit-faithful EM kernel (hap/D/D'/r2 bit-identical to the reference; slower)
 //   --gpu_stats       print pairs, EM passes and device times per GPU to stderr
+#include <errno.h>
+#include <fcntl.h>
 #include <getopt.h>
 #include <math.h>
 #include <stdio.h>
@@ -18,8 +22,10 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -29,6 +35,11 @@
 #include "ngsld_b200.h"
 
 static const char *kVersion = "1.2.1-b200";
+
+static double wall_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
 
 // fatal error in the reference's format (shared/gen_func.cpp:12-18): message, perror, exit(-1)
 [[noreturn]] static void die(const char *func, const char *msg) {
@@ -164,30 +175,53 @@ int main(int argc, char **argv) {
     o.in_probs = true;
     if (o.n_sites != (uint64_t)st.st_size / sizeof(double) / o.n_ind / 3) die(fn, "invalid/corrupt genotype input file!");
   }
-  if (o.call_geno && o.N_thresh > o.call_thresh)
-    die("call_geno", "missing data threshold must be smaller than calling genotype threshold!");
-
-  FILE *out_fh = stdout;
-  if (o.out) out_fh = fopen(o.out, "w");
-  if (!out_fh) die(fn, "cannot open output file!");
+  // Output: the reference fopen()s --out (or uses stdout) and fprintf()s under a mutex (ngsLD.cpp:73-77, 310-352).
+  // Here rows arrive as finished text in page-locked slab buffers, so the file is a plain descriptor: a regular file is
+  // written with pwrite() by several writer threads at offsets that are known as soon as all earlier slabs have been
+  // formatted; a pipe / terminal / device gets the slabs in order from one writer.
+  int out_fd = STDOUT_FILENO;
+  if (o.out) out_fd = open(o.out, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (out_fd < 0) die(fn, "cannot open output file!");
+  struct stat ost;
+  const bool seekable = fstat(out_fd, &ost) == 0 && S_ISREG(ost.st_mode);
+  auto write_all = [&](const char *p, size_t n, off_t off) -> bool {  // off < 0: sequential write()
+    while (n) {
+      const ssize_t w = off >= 0 ? pwrite(out_fd, p, n, off) : write(out_fd, p, n);
+      if (w < 0) {
+        if (errno == EINTR) continue;
+        return false;
+      }
+      p += w;
+      n -= (size_t)w;
+      if (off >= 0) off += w;
+    }
+    return true;
+  };
   char header[512];
   const int hl = ngsld_tsv_header(o.extend_out, header, sizeof header);
-  fwrite(header, 1, hl, out_fh);
+  if (!write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
 
+  const double t_start = wall_s();
   if (o.verbose >= 1) fprintf(stderr, "> Reading data from file...\n");
-  std::vector<double> raw((size_t)o.n_sites * o.n_ind * 3);
+  std::vector<double> cells((size_t)o.n_sites * o.n_ind * 3);
   int log_cells = 0;
-  if (ngsld_load_geno(o.in_geno, in_bin, o.in_probs, o.in_logscale, o.n_ind, o.n_sites, raw.data(), &log_cells) != NGSLD_OK)
+  if (ngsld_load_geno(o.in_geno, in_bin, o.in_probs, o.in_logscale, o.n_ind, o.n_sites, cells.data(), &log_cells) != NGSLD_OK)
     die_lib("read_geno");
+  const double t_read = wall_s();
   if (o.verbose >= 1 && o.call_geno) fprintf(stderr, "> Calling genotypes...\n");
   if (o.verbose >= 1) fprintf(stderr, "==> Calculating MAF for all sites...\n");
-  std::vector<double> gl(raw.size()), expg((size_t)o.n_sites * o.n_ind), maf(o.n_sites);
+  // prepared in place: the normalised likelihoods overwrite the file's cells (one genotype matrix in host memory, like
+  // the reference, instead of two)
+  std::vector<double> expg((size_t)o.n_sites * o.n_ind), maf(o.n_sites);
   const int host_threads = std::max(o.n_threads, (int)std::thread::hardware_concurrency());
-  int rc = ngsld_prepare_sites(raw.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data,
-                               o.call_geno, o.N_thresh, o.call_thresh, host_threads, gl.data(), expg.data(), maf.data());
+  int rc = ngsld_prepare_sites(cells.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data,
+                               o.call_geno, o.N_thresh, o.call_thresh, host_threads, cells.data(), expg.data(), maf.data());
   if (rc == NGSLD_E_DATA) die("read_geno", "NaN found! Is the file format correct?");
+  if (rc == NGSLD_E_INVALID && o.call_geno && o.N_thresh > o.call_thresh)  // raised by call_geno() in the reference: after the read
+    die("call_geno", "missing data threshold must be smaller than calling genotype threshold!");
   if (rc != NGSLD_OK) die(fn, "site preparation failed!");
-  std::vector<double>().swap(raw);
+  const std::vector<double> &gl = cells;
+  const double t_prep = wall_s();
 
   if (o.verbose >= 1) fprintf(stderr, "==> Getting sites coordinates\n");
   std::vector<double> pos_dist;
@@ -207,7 +241,7 @@ int main(int argc, char **argv) {
 
   const int n_dev = ngsld_device_count();
   if (n_dev < 1) die(fn, "no CUDA device available (this build has no CPU path)!");
-  int n_gpu = o.gpu_n > 0 ? std::min(o.gpu_n, n_dev) : n_dev;
+  const int n_gpu = o.gpu_n > 0 ? std::min(o.gpu_n, n_dev) : n_dev;
   if (o.verbose >= 1) fprintf(stderr, "==> Launching threads...\n");
 
   ngsld_scan_params P;
@@ -221,121 +255,211 @@ int main(int argc, char **argv) {
   P.extend_out = o.extend_out;
   P.strict = o.gpu_strict;
 
+  // ---- site table: one upload from the host, then passed on GPU to GPU (NVLink) in a doubling tree ----
   std::vector<ngsld_ctx *> ctx(n_gpu, nullptr);
-  auto setup = [&](int g) -> int {
+  const bool host_upload_all = getenv("NGSLD_CLI_HOST_UPLOAD") && atoi(getenv("NGSLD_CLI_HOST_UPLOAD"));
+  auto from_host = [&](int g) -> int {
     int r = ngsld_create(&ctx[g], g);
     if (r) return r;
     r = ngsld_set_sites(ctx[g], gl.data(), expg.data(), maf.data(), o.n_sites, o.n_ind);
     if (r) return r;
     return ngsld_set_positions(ctx[g], o.in_pos ? pos_dist.data() : nullptr, o.in_pos ? label_ptr.data() : nullptr);
   };
-  {
-    std::vector<std::thread> th;
-    std::vector<int> rcs(n_gpu, 0);
-    for (int g = 0; g < n_gpu; g++) th.emplace_back([&, g]() { rcs[g] = setup(g); });
-    for (auto &t : th) t.join();
+  auto check_setup = [&](const std::vector<int> &rcs) {
     for (int g = 0; g < n_gpu; g++)
       if (rcs[g]) {
         fprintf(stderr, "GPU %d: %s\n", g, ngsld_last_error(ctx[g]));
         die(fn, rcs[g] == NGSLD_E_DATA ? "invalid allele frequencies" : "failed to initialise the GPU engine!");
       }
+  };
+  {
+    std::vector<int> rcs(n_gpu, 0);
+    if (host_upload_all) {
+      std::vector<std::thread> th;
+      for (int g = 0; g < n_gpu; g++) th.emplace_back([&, g]() { rcs[g] = from_host(g); });
+      for (auto &t : th) t.join();
+    } else {
+      rcs[0] = from_host(0);
+      check_setup(rcs);
+      for (int have = 1; have < n_gpu; have *= 2) {  // GPUs [0, have) hold the table: each passes it on to one more
+        std::vector<std::thread> th;
+        for (int g = have; g < std::min(n_gpu, 2 * have); g++)
+          th.emplace_back([&, g, have]() {
+            rcs[g] = ngsld_create(&ctx[g], g);
+            if (!rcs[g]) rcs[g] = ngsld_share_sites(ctx[g], ctx[g - have]);
+          });
+        for (auto &t : th) t.join();
+        check_setup(rcs);
+      }
+    }
+    check_setup(rcs);
   }
-  // Work units: slabs of first sites with (about) the same number of rows.  GPUs take slabs in order from a shared
-  // counter; a writer thread appends finished slabs to the output in slab order, which is first-site order = the
-  // reference's --n_threads 1 row order.  The GPUs run at most a pool of buffers ahead of the writer, so the text held
-  // in memory stays bounded and nothing is written twice.
+  const double t_upload = wall_s();
+
+  // ---- work units: slabs of first sites with (about) the same number of rows, taken in order by the GPU threads ----
   uint64_t total_rows = 0;
   if (ngsld_scan_count(ctx[0], 0, o.n_sites, &P, &total_rows) != NGSLD_OK) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to plan the pair scan!");
   }
-  uint64_t rows_per_slab = 16ull << 20;  // a scan drains its chunk pipeline at the end: keep slabs long
+  const uint64_t row_bound = ngsld_tsv_row_bound(ctx[0], o.extend_out);
+  uint64_t buf_bytes = 1ull << 30;  // per slab buffer; a scan drains its chunk pipeline at the end, so slabs stay long
+  if (const char *e = getenv("NGSLD_CLI_BUF_MB"))
+    if (atoll(e) > 0) buf_bytes = (uint64_t)atoll(e) << 20;
+  uint64_t rows_per_slab = std::max<uint64_t>(1, std::min<uint64_t>(16ull << 20, buf_bytes / row_bound));
   if (const char *e = getenv("NGSLD_CLI_SLAB_ROWS"))  // tests: force many small slabs
     if (atoll(e) > 0) rows_per_slab = (uint64_t)atoll(e);
-  const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 16);
+  const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 20);
   std::vector<uint64_t> bounds(n_slabs + 1);
   if (ngsld_partition(ctx[0], &P, n_slabs, bounds.data()) != NGSLD_OK) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to partition the pair space!");
   }
+  // a slab holds its share of the rows plus at most the rows of one first site
+  const uint64_t slab_rows_max = std::min<uint64_t>(total_rows, (total_rows + n_slabs - 1) / n_slabs + o.n_sites + 1);
+  const uint64_t cap = std::max<uint64_t>(slab_rows_max * row_bound, 4096);
 
   if (o.verbose >= 1) fprintf(stderr, "==> Waiting for all threads to finish...\n");
+  const int n_writers = seekable ? std::max(1, std::min(n_gpu, 8)) : 1;
+  const int n_bufs = n_gpu + n_writers + 1;
+  struct Buf {
+    char *p = nullptr;
+    bool pinned = false;
+  };
+  std::vector<Buf> bufs(n_bufs);
+  for (auto &b : bufs) {
+    void *q = nullptr;
+    if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
+      b.p = (char *)q;
+      b.pinned = true;
+    } else {
+      b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
+    }
+    if (!b.p) die(fn, "cannot allocate the output buffers!");
+  }
   struct Slab {
-    std::string text;
-    bool done = false;
+    int buf = -1;
+    uint64_t bytes = 0, rows = 0;
+    off_t offset = -1;          // known once every earlier slab has been formatted
+    bool done = false, taken = false;
+    std::string spill;          // only when a slab outgrew its buffer (values the host formatter had to print)
   };
   std::vector<Slab> slab(n_slabs);
   std::mutex mu;
   std::condition_variable cv;
-  int next_slab = 0, written = 0;
+  std::vector<int> free_bufs;
+  for (int k = 0; k < n_bufs; k++) free_bufs.push_back(k);
+  int next_slab = 0, next_off = 0, next_seq = 0, written = 0;
+  off_t cursor = hl;
   bool failed = false, write_failed = false;
-  // Text buffers are recycled through a pool (no page faults on fresh memory for every slab); its size is the
-  // look-ahead window: a GPU thread that finds the pool empty waits for the writer.
-  std::vector<std::string> pool(n_gpu + 2);
   struct PerGpu {
-    uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0;
-    double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0;
+    uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0, cells = 0, cell_pairs = 0, resid = 0;
+    double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0, s_scan = 0, s_wait = 0;
   };
   std::vector<PerGpu> acc(n_gpu);
+  struct PerWriter {
+    uint64_t bytes = 0;
+    double s_write = 0;
+  };
+  std::vector<PerWriter> wacc(n_writers);
 
-  std::thread writer([&]() {
-    for (;;) {
-      std::string text;
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&]() { return failed || written == n_slabs || slab[written].done; });
-        if (failed || written == n_slabs) return;
-        text.swap(slab[written].text);
+  std::vector<std::thread> writers;
+  for (int w = 0; w < n_writers; w++)
+    writers.emplace_back([&, w]() {
+      for (;;) {
+        int k = -1;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() {
+            if (failed || written == n_slabs) return true;
+            if (!seekable) return next_seq < next_off && !slab[next_seq].taken;
+            for (int j = written; j < next_off; j++)
+              if (!slab[j].taken) return true;
+            return false;
+          });
+          if (failed || written == n_slabs) return;
+          if (!seekable) {
+            k = next_seq;
+          } else {
+            for (int j = written; j < next_off && k < 0; j++)
+              if (!slab[j].taken) k = j;
+          }
+          slab[k].taken = true;
+        }
+        const double t0 = wall_s();
+        const char *src = slab[k].spill.empty() ? bufs[slab[k].buf].p : slab[k].spill.data();
+        const bool ok = write_all(src, slab[k].bytes, seekable ? slab[k].offset : -1);
+        wacc[w].s_write += wall_s() - t0;
+        wacc[w].bytes += slab[k].bytes;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          if (!ok) failed = write_failed = true;
+          free_bufs.push_back(slab[k].buf);
+          std::string().swap(slab[k].spill);
+          if (!seekable) next_seq++;
+          written++;  // writers take the lowest slab not yet taken, so every slab below index `written` is taken
+        }
+        cv.notify_all();
       }
-      const bool ok = fwrite(text.data(), 1, text.size(), out_fh) == text.size();
-      text.clear();  // keeps the capacity
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!ok) failed = write_failed = true;
-        written++;
-        pool.emplace_back(std::move(text));
-      }
-      cv.notify_all();
-    }
-  });
+    });
+
   auto append_sink = [](void *user, const char *bytes, uint64_t n_bytes, uint64_t) -> int {
     ((std::string *)user)->append(bytes, n_bytes);
     return 0;
   };
   std::vector<int> rcs(n_gpu, 0);
+  const double t_scan0 = wall_s();
   {
     std::vector<std::thread> th;
     for (int g = 0; g < n_gpu; g++)
       th.emplace_back([&, g]() {
         for (;;) {
-          int k;
-          std::string text;
+          int k, bi;
+          const double tw0 = wall_s();
           {
             std::unique_lock<std::mutex> lk(mu);
-            // slabs must be claimed in order by whoever holds a buffer, or the writer could starve for the next slab
-            cv.wait(lk, [&]() { return failed || next_slab >= n_slabs || !pool.empty(); });
+            // slabs are claimed in order by whoever holds a buffer, or the writers could starve for the next slab
+            cv.wait(lk, [&]() { return failed || next_slab >= n_slabs || !free_bufs.empty(); });
             if (failed || next_slab >= n_slabs) return;
             k = next_slab++;
-            text.swap(pool.back());
-            pool.pop_back();
+            bi = free_bufs.back();
+            free_bufs.pop_back();
           }
-          uint64_t rows = 0;
-          if (ngsld_scan_count(ctx[g], bounds[k], bounds[k + 1], &P, &rows) == NGSLD_OK)
-            text.reserve(rows * (o.extend_out ? 176 : 96) + 4096);  // typical row length; append() grows it if needed
-          const int rc = ngsld_scan_tsv(ctx[g], bounds[k], bounds[k + 1], &P, append_sink, &text);
+          const double ts0 = wall_s();
+          acc[g].s_wait += ts0 - tw0;
+          uint64_t nb = 0, nr = 0;
+          std::string spill;
+          int rc = ngsld_scan_tsv_into(ctx[g], bounds[k], bounds[k + 1], &P, bufs[bi].p, cap, &nb, &nr);
           ngsld_scan_stats st;
           ngsld_get_stats(ctx[g], &st);
+          if (rc == NGSLD_E_INVALID && strstr(ngsld_last_error(ctx[g]), "too small")) {
+            // rows longer than the device formatter's bound (host-formatted values): take this slab through the sink
+            rc = ngsld_scan_tsv(ctx[g], bounds[k], bounds[k + 1], &P, append_sink, &spill);
+            ngsld_get_stats(ctx[g], &st);
+            nb = spill.size();
+            nr = st.n_pairs;
+          }
+          acc[g].s_scan += wall_s() - ts0;
           acc[g].pairs += st.n_pairs; acc[g].passes += st.sum_em_passes; acc[g].launches += st.n_launches; acc[g].slabs++;
           acc[g].ms_device += st.ms_device_total; acc[g].ms_em += st.ms_em; acc[g].ms_pearson += st.ms_pearson;
-          acc[g].ms_format += st.ms_format;
+          acc[g].ms_format += st.ms_format; acc[g].cells += st.sum_cells; acc[g].cell_pairs += st.n_cell_pairs;
+          acc[g].resid += st.n_resid_pairs;
           {
             std::lock_guard<std::mutex> lk(mu);
             if (rc) {
               rcs[g] = rc;
               failed = true;
             } else {
-              slab[k].text.swap(text);
+              slab[k].buf = bi;
+              slab[k].bytes = nb;
+              slab[k].rows = nr;
+              slab[k].spill.swap(spill);
               slab[k].done = true;
+              while (next_off < n_slabs && slab[next_off].done && slab[next_off].offset < 0) {
+                slab[next_off].offset = cursor;
+                cursor += (off_t)slab[next_off].bytes;
+                next_off++;
+              }
             }
           }
           cv.notify_all();
@@ -344,24 +468,43 @@ int main(int argc, char **argv) {
       });
     for (auto &t : th) t.join();
   }
+  const double t_scan1 = wall_s();
   cv.notify_all();
-  writer.join();
+  for (auto &t : writers) t.join();
+  const double t_done = wall_s();
   for (int g = 0; g < n_gpu; g++)
     if (rcs[g]) {
       fprintf(stderr, "GPU %d: %s\n", g, ngsld_last_error(ctx[g]));
       die(fn, "pair scan failed!");
     }
   if (write_failed) die(fn, "cannot write output!");
-  if (o.gpu_stats)
-    for (int g = 0; g < n_gpu; g++)
-      fprintf(stderr, "[gpu %d] %lu slabs of %d: %lu pairs, %lu EM passes, %lu launches, scan %.1f ms incl. waiting for the writer (EM %.1f, r2_ExpG %.1f, format %.1f), %.0f pairs/s\n",
-              g, acc[g].slabs, n_slabs, acc[g].pairs, acc[g].passes, acc[g].launches, acc[g].ms_device, acc[g].ms_em, acc[g].ms_pearson,
-              acc[g].ms_format, acc[g].ms_device > 0 ? acc[g].pairs / (acc[g].ms_device * 1e-3) : 0.0);
+  if (o.gpu_stats) {
+    uint64_t all_pairs = 0;
+    for (int g = 0; g < n_gpu; g++) {
+      all_pairs += acc[g].pairs;
+      fprintf(stderr, "[gpu %d] %lu slabs of %d: %lu pairs, %lu EM passes, %lu launches, scanning %.2f s (device %.1f ms: EM %.1f, r2_ExpG %.1f, format %.1f), waiting for a buffer %.2f s, %.0f pairs/s while scanning",
+              g, acc[g].slabs, n_slabs, acc[g].pairs, acc[g].passes, acc[g].launches, acc[g].s_scan, acc[g].ms_device, acc[g].ms_em,
+              acc[g].ms_pearson, acc[g].ms_format, acc[g].s_wait, acc[g].s_scan > 0 ? acc[g].pairs / acc[g].s_scan : 0.0);
+      if (acc[g].cell_pairs)
+        fprintf(stderr, "; class-compressed EM: %.1f cells per pair, %lu pairs left to the dense kernel", (double)acc[g].cells / acc[g].cell_pairs, acc[g].resid);
+      fprintf(stderr, "\n");
+    }
+    for (int w = 0; w < n_writers; w++)
+      fprintf(stderr, "[writer %d] %.2f GB in %.2f s of %s = %.2f GB/s\n", w, wacc[w].bytes / 1e9, wacc[w].s_write,
+              seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
+    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s)\n",
+            t_read - t_start, t_prep - t_read, n_gpu, t_upload - t_prep, host_upload_all || n_gpu == 1 ? "from the host" : "one upload, then GPU to GPU",
+            t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - hl) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
+            bufs[0].pinned ? "page-locked" : "pageable");
+  }
   if (o.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   for (auto c : ctx) ngsld_destroy(c);
+  for (auto &b : bufs) {
+    if (b.pinned) ngsld_free_host(b.p);
+    else free(b.p);
+  }
   ngsld_free(label_blob);
-  if (out_fh != stdout) fclose(out_fh);
-  else fflush(stdout);
+  if (out_fd != STDOUT_FILENO && close(out_fd) != 0) die(fn, "cannot write output!");
   if (o.verbose >= 1) fprintf(stderr, "Done!\n");
   return 0;
 }

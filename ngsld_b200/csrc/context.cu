@@ -103,6 +103,7 @@ struct ngsld_ctx {
   char *d_label_blob = nullptr;
   uint32_t *d_label_off = nullptr;  // n_sites + 1
   uint32_t max_label_len = 6;       // "(null)"
+  size_t label_blob_bytes = 0;
   // plan buffers
   uint32_t *d_cs = nullptr, *d_cw_end = nullptr;
   unsigned long long *d_row_off = nullptr, *d_seeds = nullptr, *d_counts = nullptr;
@@ -193,6 +194,44 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
   c->alloc_host = need_host && !need_text;
   c->alloc_text = need_text;
   c->alloc_slot = need_text ? slot : 0;
+  return NGSLD_OK;
+}
+
+// Device buffers of the site table for a given shape (kept when the shape is unchanged).  with_expg: also the
+// expected-genotype matrix, which only ngsld_set_sites needs (input of the per-site x87 recurrence).
+int alloc_site_buffers(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind, bool with_expg) {
+  const uint64_t n_pad = (n_ind + 1) & ~1ull, n_cpad = (n_ind + 15) & ~15ull;
+  const size_t row_bytes = n_pad * 24;
+  if (n_sites != c->n_sites || n_ind != c->n_ind || !c->d_gl) {
+    dfree(c->d_gl);
+    dfree(c->d_maf);
+    dfree(c->d_q);
+    dfree(c->d_dx_sig);
+    dfree(c->d_dx_se);
+    dfree(c->d_seg);
+    dfree(c->d_expg);
+    dfree(c->d_ratio);
+    dfree(c->d_cls);
+    dfree(c->d_pal);
+    dfree(c->d_pal_k);
+    dfree(c->d_pal_miss);
+    c->n_sites = c->n_ind = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
+    CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * n_pad * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * n_pad * sizeof(uint16_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_pad * sizeof(uint64_t)));
+    if (n_ind < 65536) {  // joint-class counters are 16 bits wide
+      CUDA_TRY(c, cudaMalloc(&c->d_cls, n_sites * n_cpad));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal, n_sites * (size_t)NGSLD_KMAX * 3 * sizeof(double)));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal_k, n_sites));
+      CUDA_TRY(c, cudaMalloc(&c->d_pal_miss, n_sites * sizeof(uint64_t)));
+    }
+    if (!c->d_cell_stats) CUDA_TRY(c, cudaMalloc(&c->d_cell_stats, 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int)));
+  }
+  if (with_expg && !c->d_expg) CUDA_TRY(c, cudaMalloc(&c->d_expg, n_sites * n_ind * sizeof(double)));
   return NGSLD_OK;
 }
 
@@ -541,17 +580,19 @@ int choose_cell(ngsld_ctx *c, EmChoice &ch) {
   if (!(path ? c->cell_possible : c->cell_ok)) return NGSLD_OK;
   // cells per lane in registers from the sampled 99.5th percentile; the rest of a pair's cells go to shared memory
   int r = c->cell_p995 <= 64 ? 2 : c->cell_p995 <= 128 ? 4 : 6;
+  int minb = 4;  // CTAs per SM the variant is compiled for: 4 -> 128 registers, 16 warps per SM (measured +14 % over 3 -> 168)
   if (const char *e = getenv("NGSLD_CELL_R")) r = atoi(e);
+  if (const char *e = getenv("NGSLD_CELL_MINB")) minb = atoi(e);
   const emcell::CellVariant *v = nullptr;
   for (int k = 0; k < emcell::cell_variants_count; k++)
-    if (emcell::cell_variants[k].r == r) v = &emcell::cell_variants[k];
-  if (!v) v = &emcell::cell_variants[emcell::cell_variants_count - 1];
+    if (emcell::cell_variants[k].r == r && (!v || emcell::cell_variants[k].minb == minb)) v = &emcell::cell_variants[k];
+  if (!v) v = &emcell::cell_variants[emcell::cell_variants_count - 2];
   r = v->r;
-  uint32_t tcap = c->cell_p995 > 32u * r ? ((c->cell_p995 - 32u * r + 31u) & ~31u) : 0u;
-  tcap = std::max<uint32_t>(tcap, 32);  // room for the odd pair beyond the sampled percentile
-  if (const char *e = getenv("NGSLD_CELL_TCAP")) tcap = ((uint32_t)atoi(e) + 31u) & ~31u;
+  uint32_t tcap = c->cell_p995 > 32u * r ? ((c->cell_p995 - 32u * r + 63u) & ~63u) : 0u;
+  tcap = std::max<uint32_t>(tcap, 64);  // room for the odd pair beyond the sampled percentile
+  if (const char *e = getenv("NGSLD_CELL_TCAP")) tcap = ((uint32_t)atoi(e) + 63u) & ~63u;
   // at least two CTAs per SM: shrink the tail if it does not fit (pairs beyond it go to the dense kernel)
-  while (tcap > 0 && 2 * (emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap) + 1024) > (size_t)c->smem_optin) tcap -= 32;
+  while (tcap > 0 && 2 * (emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap) + 1024) > (size_t)c->smem_optin) tcap -= 64;
   const size_t smem = emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap);
   if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
   int occ = 0;
@@ -676,7 +717,8 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   if (P.strict || (ch.v == nullptr && ch.w == nullptr))
     snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "aux::em_strict_kernel");
   else if (use_cell)
-    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emcell::em_cell_kernel<R=%d,FUSE=%d>", ch.cell->r, fused ? 1 : 0);
+    snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emcell::em_cell_kernel<R=%d,FUSE=%d,MINB=%d>", ch.cell->r, fused ? 1 : 0,
+             ch.cell->minb);
   else if (ch.w)
     snprintf(c->stats.em_kernel, sizeof c->stats.em_kernel, "emwarp::em_warp_kernel<R=%d,G=%d>", ch.w->r, ch.w->g);
   else
@@ -758,6 +800,10 @@ struct Delivery {
   ngsld_row_sink rows;
   ngsld_text_sink text;
   void *user;
+  // MODE_TEXT without a sink: the text goes straight from the device into one caller buffer (ngsld_scan_tsv_into)
+  char *text_dst = nullptr;
+  uint64_t text_cap = 0;
+  uint64_t *text_len = nullptr;
 };
 
 int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
@@ -772,9 +818,16 @@ int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
     unsigned long long bytes = b.h_text_len[0];
     static const bool force_host = getenv("NGSLD_FORCE_HOST_FORMAT") && atoi(getenv("NGSLD_FORCE_HOST_FORMAT"));  // tests
     if (b.h_text_len[1] == 0 && !force_host) {
-      CUDA_TRY(c, cudaMemcpyAsync(b.h_text, b.d_text_out, bytes, cudaMemcpyDeviceToHost, c->s_copy));
+      char *dst = b.h_text;
+      if (d.text_dst) {  // no staging: device -> the caller's (page-locked) buffer at its running offset
+        if (*d.text_len + bytes > d.text_cap) return fail(c, NGSLD_E_INVALID, "text buffer too small for this scan");
+        dst = d.text_dst + *d.text_len;
+        *d.text_len += bytes;
+      }
+      CUDA_TRY(c, cudaMemcpyAsync(dst, b.d_text_out, bytes, cudaMemcpyDeviceToHost, c->s_copy));
       CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
       c->stats.d2h_bytes += bytes + 16;
+      if (d.text_dst) return NGSLD_OK;
     } else {
       // some value was outside the device formatter's range: re-format this chunk with the host printf
       CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, b.n_rows * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
@@ -789,6 +842,12 @@ int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
         const int m = fmt::format_row_host(r, l1, l2, c->h_maf[r.s1], c->h_maf[r.s2], d.extend_out, line, sizeof line);
         if (m < 0) return fail(c, NGSLD_E_INVALID, "row too long for the host formatter");
         txt.append(line, m);
+      }
+      if (d.text_dst) {
+        if (*d.text_len + txt.size() > d.text_cap) return fail(c, NGSLD_E_INVALID, "text buffer too small for this scan");
+        memcpy(d.text_dst + *d.text_len, txt.data(), txt.size());
+        *d.text_len += txt.size();
+        return NGSLD_OK;
       }
       if (d.text && d.text(d.user, txt.data(), txt.size(), b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "text sink aborted the scan");
       return NGSLD_OK;
@@ -1065,36 +1124,8 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
   const uint64_t n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
   const uint64_t n_cpad = (n_ind + 15) & ~15ull;  // class rows (one byte per individual) are read as 32-bit words
   const size_t row_bytes = n_pad * 24;
-  if (n_sites != c->n_sites || n_ind != c->n_ind || !c->d_gl) {  // same shape as last time: keep the device buffers
-    dfree(c->d_gl);
-    dfree(c->d_maf);
-    dfree(c->d_q);
-    dfree(c->d_dx_sig);
-    dfree(c->d_dx_se);
-    dfree(c->d_seg);
-    dfree(c->d_expg);
-    dfree(c->d_ratio);
-    dfree(c->d_cls);
-    dfree(c->d_pal);
-    dfree(c->d_pal_k);
-    dfree(c->d_pal_miss);
-    c->n_sites = c->n_ind = 0;
-    CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
-    CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * n_pad * sizeof(uint64_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * n_pad * sizeof(uint16_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_expg, n_sites * n_ind * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_pad * sizeof(uint64_t)));
-    if (n_ind < 65536) {  // joint-class counters are 16 bits wide
-      CUDA_TRY(c, cudaMalloc(&c->d_cls, n_sites * n_cpad));
-      CUDA_TRY(c, cudaMalloc(&c->d_pal, n_sites * (size_t)NGSLD_KMAX * 3 * sizeof(double)));
-      CUDA_TRY(c, cudaMalloc(&c->d_pal_k, n_sites));
-      CUDA_TRY(c, cudaMalloc(&c->d_pal_miss, n_sites * sizeof(uint64_t)));
-    }
-    if (!c->d_cell_stats) CUDA_TRY(c, cudaMalloc(&c->d_cell_stats, 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int)));
-  }
+  int rc_alloc = alloc_site_buffers(c, n_sites, n_ind, true);  // same shape as last time: the device buffers are kept
+  if (rc_alloc) return rc_alloc;
   c->n_sites = n_sites;
   c->n_ind = n_ind;
   c->n_pad = n_pad;
@@ -1222,6 +1253,7 @@ int ngsld_set_positions(ngsld_ctx *c, const double *pos_dist, const char *const 
     CUDA_TRY(c, cudaMemcpy(c->d_label_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->d_label_off, off.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
     c->have_labels = true;
+    c->label_blob_bytes = blob.size();
     c->max_label_len = std::max<uint32_t>(mx, 1);
   }
   return NGSLD_OK;
@@ -1418,6 +1450,122 @@ int ngsld_scan_tsv(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_sca
   d.text = sink;
   d.user = user;
   return run_scan(c, s1_lo, s1_hi, p, d);
+}
+
+int ngsld_scan_tsv_into(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, char *buf, uint64_t cap,
+                        uint64_t *n_bytes, uint64_t *n_rows) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!buf && cap) return fail(c, NGSLD_E_INVALID, "text buffer missing");
+  uint64_t len = 0;
+  Delivery d;
+  d.mode = MODE_TEXT;
+  d.extend_out = p ? p->extend_out : 0;
+  d.rows = nullptr;
+  d.text = nullptr;
+  d.user = nullptr;
+  d.text_dst = buf ? buf : (char *)&len;  // cap 0: any row makes the scan fail with "too small"
+  d.text_cap = cap;
+  d.text_len = &len;
+  const int rc = run_scan(c, s1_lo, s1_hi, p, d);
+  if (n_bytes) *n_bytes = len;
+  if (n_rows) *n_rows = c->stats.n_pairs;
+  return rc;
+}
+
+uint64_t ngsld_tsv_row_bound(const ngsld_ctx *c, int extend_out) {
+  return fmt::slot_bytes(c ? c->max_label_len : 6, extend_out != 0);
+}
+
+int ngsld_alloc_host(void **p, size_t bytes) {
+  if (!p) return NGSLD_E_INVALID;
+  *p = nullptr;
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+    *p = nullptr;
+    return e == cudaErrorMemoryAllocation ? NGSLD_E_NOMEM : NGSLD_E_CUDA;
+  }
+  return NGSLD_OK;
+}
+
+void ngsld_free_host(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// Device-to-device copy of everything ngsld_set_sites + ngsld_set_positions put on src's GPU (NVLink when the two
+// devices are peers), instead of a second upload from the host.
+int ngsld_share_sites(ngsld_ctx *dst, const ngsld_ctx *src) {
+  if (!dst || !src) return NGSLD_E_INVALID;
+  ngsld_ctx *c = dst;
+  if (dst == src) return NGSLD_OK;
+  if (!src->d_gl) return fail(c, NGSLD_E_INVALID, "the source context holds no sites");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  if (c->device != src->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->device, src->device);
+    if (can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, NGSLD_E_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();  // "already enabled" is not an error
+    }
+  }
+  int rc = alloc_site_buffers(c, src->n_sites, src->n_ind, false);
+  if (rc) return rc;
+  const uint64_t n = src->n_sites, n_pad = src->n_pad, n_cpad = src->n_cpad;
+  c->n_sites = n;
+  c->n_ind = src->n_ind;
+  c->n_pad = n_pad;
+  c->n_cpad = n_cpad;
+  uint64_t moved = 0;
+  auto peer = [&](void *to, const void *from, size_t bytes) -> cudaError_t {
+    moved += bytes;
+    return cudaMemcpyPeerAsync(to, c->device, from, src->device, bytes, c->s_main);
+  };
+  CUDA_TRY(c, peer(c->d_gl, src->d_gl, n * n_pad * 24));
+  CUDA_TRY(c, peer(c->d_maf, src->d_maf, n * 8));
+  CUDA_TRY(c, peer(c->d_q, src->d_q, n * 8));
+  CUDA_TRY(c, peer(c->d_dx_sig, src->d_dx_sig, n * n_pad * 8));
+  CUDA_TRY(c, peer(c->d_dx_se, src->d_dx_se, n * n_pad * 2));
+  CUDA_TRY(c, peer(c->d_seg, src->d_seg, n * 4));
+  CUDA_TRY(c, peer(c->d_ratio, src->d_ratio, n_pad * 8));
+  if (c->d_cls && src->d_cls) {
+    CUDA_TRY(c, peer(c->d_cls, src->d_cls, n * n_cpad));
+    CUDA_TRY(c, peer(c->d_pal, src->d_pal, n * (size_t)NGSLD_KMAX * 24));
+    CUDA_TRY(c, peer(c->d_pal_k, src->d_pal_k, n));
+    CUDA_TRY(c, peer(c->d_pal_miss, src->d_pal_miss, n * 8));
+  }
+  dfree(c->d_cum);
+  dfree(c->d_label_blob);
+  dfree(c->d_label_off);
+  if (src->have_pos) {
+    CUDA_TRY(c, cudaMalloc(&c->d_cum, n * sizeof(double)));
+    CUDA_TRY(c, peer(c->d_cum, src->d_cum, n * 8));
+  }
+  if (src->have_labels) {
+    CUDA_TRY(c, cudaMalloc(&c->d_label_blob, std::max<size_t>(src->label_blob_bytes, 1)));
+    CUDA_TRY(c, cudaMalloc(&c->d_label_off, (n + 1) * sizeof(uint32_t)));
+    if (src->label_blob_bytes) CUDA_TRY(c, peer(c->d_label_blob, src->d_label_blob, src->label_blob_bytes));
+    CUDA_TRY(c, peer(c->d_label_off, src->d_label_off, (n + 1) * 4));
+  }
+  c->h_maf = src->h_maf;
+  c->h_cum = src->h_cum;
+  c->h_seg = src->h_seg;
+  c->h_labels = src->h_labels;
+  c->have_pos = src->have_pos;
+  c->have_labels = src->have_labels;
+  c->max_label_len = src->max_label_len;
+  c->label_blob_bytes = src->label_blob_bytes;
+  c->cell_ok = src->cell_ok;
+  c->cell_possible = src->cell_possible && c->d_cls;
+  c->cell_mean = src->cell_mean;
+  c->cell_uncoded_frac = src->cell_uncoded_frac;
+  c->cell_p995 = src->cell_p995;
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+  memset(&c->stats, 0, sizeof c->stats);
+  c->stats.h2d_bytes = 0;
+  c->stats.d2h_bytes = moved;  // reported as bytes moved between devices
+  return NGSLD_OK;
 }
 
 int ngsld_scan_device(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p) {

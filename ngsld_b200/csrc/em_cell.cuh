@@ -42,7 +42,7 @@ using emfast::estep;
 
 struct CellArgs {
   uint32_t *resid;    // [chunk rows] indices (inside the chunk) of the pairs left to the dense kernel
-  uint32_t tcap;      // cells a warp can hold in shared memory beyond its 32 R register cells (multiple of 32)
+  uint32_t tcap;      // cells a warp can hold in shared memory beyond its 32 R register cells (multiple of 64)
   int ignore_miss;    // --ignore_miss_data: individuals whose class is flat at either site are left out
   int fuse_pearson;   // compute r2_ExpG in this kernel
 };
@@ -133,10 +133,72 @@ __device__ __forceinline__ void cell_step(const double f0, const double f1, cons
   a3 = __fma_rn(i3, wi, a3);
 }
 
-// R  cells per lane held in registers (cell slot lane + 32 r); a pair may have up to 32 R + A.tcap cells.
-// Three CTAs of four warps per SM: 168 registers per thread.
-template <int R, bool FUSE>
-__global__ void __launch_bounds__(CTA_THREADS, 3) em_cell_kernel(SiteTable T, PairChunk C, CellArgs A, DevCounters *ctr) {
+// Sum of a0..a3 over the warp, transposed: lane l receives the total of component q(l) = 2 * bit4(l) + bit3(l) only
+// (lanes 0-7: a0, 8-15: a1, 16-23: a2, 24-31: a3).  Same butterfly as emfast::group_sum4 without its final four
+// broadcasts; every lane of a quadrant ends up with identical bits (each round adds the two partners' values in both).
+__device__ __forceinline__ double warp_sum4_own(double a0, double a1, double a2, double a3, int lane) {
+  const bool hi = lane & 16, lo = lane & 8;
+  double x0 = hi ? a2 : a0, x1 = hi ? a3 : a1;
+  const double y0 = hi ? a0 : a2, y1 = hi ? a1 : a3;
+  x0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+  x1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+  double z = lo ? x1 : x0;
+  const double w = lo ? x0 : x1;
+  z += __shfl_xor_sync(0xffffffffu, w, 8);
+  z += __shfl_xor_sync(0xffffffffu, z, 4);
+  z += __shfl_xor_sync(0xffffffffu, z, 2);
+  z += __shfl_xor_sync(0xffffffffu, z, 1);
+  return z;
+}
+
+// The EM of one pair on its cells: L register levels in use (straight-line, so that the L independent dependency chains
+// interleave -- a branch per level would serialise them) + the shared-memory tail.  Per pass every lane performs the
+// M-step and the convergence test of ITS OWN frequency component only (f_q <- f_q A_q / n_used with A_q the warp total
+// of component q, see warp_sum4_own) and the four new frequencies are then broadcast; `fq` / `Aq` are the lane's own
+// component.  Convergence (reference gen_func.cpp:1049-1055): eps = max_k |f_k - f_last_k| < 1e-5 with a NaN difference
+// never raising eps  <=>  no component has |difference| >= 1e-5.  Returns the index of the converging pass.
+template <int L, int R>
+__device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double *tail, uint32_t tcap, uint32_t n_tail_pad,
+                                               double inv_x, int lane, double &f0, double &f1, double &f2, double &f3,
+                                               double &Aq, bool &conv) {
+  double fq = (lane & 16) ? ((lane & 8) ? f3 : f2) : ((lane & 8) ? f1 : f0);
+  uint32_t it = 0;
+  for (;;) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int r = 0; r < L; r++) cell_step(f0, f1, f2, f3, g[r], a0, a1, a2, a3);
+    for (uint32_t t = lane; t < n_tail_pad; t += 64u) {  // two cells per lane and trip
+      Cell c, d;
+      c.g.p0 = tail[0 * tcap + t]; c.g.p1 = tail[1 * tcap + t]; c.g.p2 = tail[2 * tcap + t];
+      c.g.q0 = tail[3 * tcap + t]; c.g.q1 = tail[4 * tcap + t]; c.g.q2 = tail[5 * tcap + t];
+      c.w = tail[6 * tcap + t];
+      const uint32_t u = t + 32u;
+      d.g.p0 = tail[0 * tcap + u]; d.g.p1 = tail[1 * tcap + u]; d.g.p2 = tail[2 * tcap + u];
+      d.g.q0 = tail[3 * tcap + u]; d.g.q1 = tail[4 * tcap + u]; d.g.q2 = tail[5 * tcap + u];
+      d.w = tail[6 * tcap + u];
+      cell_step(f0, f1, f2, f3, c, a0, a1, a2, a3);
+      cell_step(f0, f1, f2, f3, d, a0, a1, a2, a3);
+    }
+    const double z = warp_sum4_own(a0, a1, a2, a3, lane);
+    Aq = fq * z;
+    const double nq = Aq * inv_x;
+    const bool moved = fabs(nq - fq) >= NGSLD_EPS;  // false for a NaN difference
+    fq = nq;
+    f0 = __shfl_sync(0xffffffffu, nq, 0);
+    f1 = __shfl_sync(0xffffffffu, nq, 8);
+    f2 = __shfl_sync(0xffffffffu, nq, 16);
+    f3 = __shfl_sync(0xffffffffu, nq, 24);
+    conv = !__any_sync(0xffffffffu, moved);
+    if (conv || it == NGSLD_ITER_MAX - 1) break;
+    it++;
+  }
+  return it;
+}
+
+// R     cells per lane held in registers (cell slot lane + 32 r); a pair may have up to 32 R + A.tcap cells.
+// MINB  CTAs (of four warps) per SM the register allocation aims at: 3 -> 168 registers per thread, 4 -> 128.
+template <int R, bool FUSE, int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T, PairChunk C, CellArgs A, DevCounters *ctr) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t cap = 32u * R + A.tcap;
@@ -193,7 +255,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) em_cell_kernel(SiteTable T, Pa
         if (slot < n_cells) cell_load(g[r], T, s1, s2, keys[slot], bins);
       }
       const uint32_t n_tail = n_cells > 32u * R ? n_cells - 32u * R : 0u;
-      const uint32_t n_tail_pad = (n_tail + 31u) & ~31u;  // whole warps: the last one is filled up with empty cells
+      const uint32_t n_tail_pad = (n_tail + 63u) & ~63u;  // two cells per lane and trip: filled up with empty cells
+      const uint32_t n_lev = n_cells >= 32u * R ? (uint32_t)R : (n_cells + 31u) / 32u;  // register levels in use
       for (uint32_t t = lane; t < n_tail_pad; t += 32u) {
         Cell c;
         cell_default(c);
@@ -210,35 +273,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) em_cell_kernel(SiteTable T, Pa
       double f1 = __dmul_rn(__dsub_rn(1.0, m1), m2);
       double f2 = __dmul_rn(m1, __dsub_rn(1.0, m2));
       double f3 = __dmul_rn(m1, m2);
-      double A0 = 0, A1 = 0, A2 = 0, A3 = 0;
+      double Aq = 0;
       uint32_t it = 0;
       bool conv = false;
-      for (;;) {
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (32u * r < n_cells) cell_step(f0, f1, f2, f3, g[r], a0, a1, a2, a3);  // warp-uniform: skips empty levels
-        for (uint32_t t = lane; t < n_tail_pad; t += 32u) {
-          Cell c;
-          c.g.p0 = tail[0 * A.tcap + t]; c.g.p1 = tail[1 * A.tcap + t]; c.g.p2 = tail[2 * A.tcap + t];
-          c.g.q0 = tail[3 * A.tcap + t]; c.g.q1 = tail[4 * A.tcap + t]; c.g.q2 = tail[5 * A.tcap + t];
-          c.w = tail[6 * A.tcap + t];
-          cell_step(f0, f1, f2, f3, c, a0, a1, a2, a3);
-        }
-        emfast::group_sum4<32>(a0, a1, a2, a3, lane);
-        // ---- M-step and convergence test (reference gen_func.cpp:1049-1055: eps = max |f - f_last| < 1e-5) ----
-        A0 = f0 * a0; A1 = f1 * a1; A2 = f2 * a2; A3 = f3 * a3;
-        const double n0 = A0 * inv_x, n1 = A1 * inv_x, n2 = A2 * inv_x, n3 = A3 * inv_x;
-        // eps starts at 0 and a NaN difference never raises it (the reference's `if (d > eps)` chain)
-        double eps = fmax(0.0, fabs(n0 - f0));
-        eps = fmax(eps, fabs(n1 - f1));
-        eps = fmax(eps, fabs(n2 - f2));
-        eps = fmax(eps, fabs(n3 - f3));
-        f0 = n0; f1 = n1; f2 = n2; f3 = n3;
-        conv = eps < NGSLD_EPS;
-        if (conv || it == NGSLD_ITER_MAX - 1) break;
-        it++;
+      switch (n_lev) {  // warp-uniform; empty register levels are skipped as a whole
+        case 0: it = em_iterate<0, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 1: it = em_iterate<1, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 2: it = em_iterate<(R < 2 ? R : 2), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 3: it = em_iterate<(R < 3 ? R : 3), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 4: it = em_iterate<(R < 4 ? R : 4), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 5: it = em_iterate<(R < 5 ? R : 5), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        default: it = em_iterate<R, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
       }
+      const double A0 = __shfl_sync(0xffffffffu, Aq, 0), A1 = __shfl_sync(0xffffffffu, Aq, 8),
+                   A2 = __shfl_sync(0xffffffffu, Aq, 16), A3 = __shfl_sync(0xffffffffu, Aq, 24);
       if (lane == 0) {
         // Output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113): true divisions and the
         // sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes.
@@ -279,7 +327,7 @@ __global__ void __launch_bounds__(CTA_THREADS) cell_stats_kernel(SiteTable T, ui
                                   unsigned int *hist);
 
 struct CellVariant {
-  int r;
+  int r, minb;  // cells per lane in registers, CTAs per SM the kernel was compiled for
   const void *fn, *fn_fused;
 };
 extern const CellVariant cell_variants[];

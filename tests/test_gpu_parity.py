@@ -271,3 +271,33 @@ def test_text_buffers_follow_the_row_slot_size(G, tmp_path_factory):
     for la, lb in zip(short[:200], d.decode().splitlines()[1:201]):
         fa, fb = la.split("\t"), lb.split("\t")
         assert fb[0] == fa[0] + ":" + "x" * 40 and fb[1] == fa[1] + ":" + "x" * 40 and fa[2:] == fb[2:]
+
+
+def test_text_into_one_buffer_and_shared_site_table(G, tmp_path_factory):
+    """ngsld_scan_tsv_into (device -> one caller buffer, page-locked or pageable) gives the bytes of ngsld_scan_tsv, and a
+    context that received its site table from another context by device-to-device copy (ngsld_share_sites) scans to the
+    same bytes as the one that was fed from the host."""
+    tmp = tmp_path_factory.getbasetemp()
+    v = H.MANIFEST["fixtures"]["s"]["variants"]["ext"]
+    raw, labels, dist, opt = H.load_fixture("s", tmp, v["flags"], True)
+    eng, _ = G.engine_for(raw, opt, labels, dist)
+    with eng:
+        for strict in (True, False):
+            p = G.scan_params(opt, strict)
+            whole = eng.scan_tsv(p, header=False)
+            for pinned in (True, False):
+                text, n_rows = eng.scan_tsv_into(p, pinned=pinned)
+                assert n_rows == v["rows"] and text == whole
+            eng.set_chunk_rows(1000)
+            assert eng.scan_tsv_into(p)[0] == whole
+            eng.set_chunk_rows(0)
+        assert H.md5(N.tsv_header(True) + eng.scan_tsv_into(G.scan_params(opt, True))[0]) == v["md5"]
+        n_dev = N.load_library().ngsld_device_count()
+        for dev in sorted({0, n_dev - 1}):
+            with N.Engine(dev) as other:
+                other.share_sites_from(eng)
+                for strict in (True, False):
+                    p = G.scan_params(opt, strict)
+                    assert other.scan_tsv(p) == eng.scan_tsv(p)
+                q = G.scan_params(dict(opt, max_kb_dist=20, rnd_sample=0.5, seed=3), False)
+                assert other.scan(q).tobytes() == eng.scan(q).tobytes()

@@ -172,11 +172,12 @@ def test_decay_bins_equal_numpy_binning_of_the_rows(bin_size, n_bins, kw):
         assert np.allclose(bins["sum"][:, j], tot, rtol=1e-9, atol=1e-12), f
 
 
-@pytest.mark.parametrize("flags,max_cells", [(["--call_geno"], 9), (["--call_geno", "--N_thresh", "0.4", "--call_thresh", "0.4"], 16)])
+@pytest.mark.parametrize("flags,max_cells", [(["--call_geno"], 16), (["--call_geno", "--N_thresh", "0.4", "--call_thresh", "0.4"], 16)])
 def test_called_genotypes_run_on_a_count_table(G, flags, max_cells):
-    """--call_geno (reference gen_func.cpp:886-914) makes every likelihood triple one-hot (or flat below N_thresh): a
-    pair then has at most 3 x 3 (4 x 4) distinct combinations and the class-compressed EM iterates on that count table,
-    whatever the sample size.  Same nIter, 1e-9, as for any other input."""
+    """--call_geno (reference gen_func.cpp:886-914) makes every likelihood triple one-hot, or flat for an individual
+    without data (flat triples stay flat: `best = -1`) or below N_thresh: a pair then has at most 4 x 4 distinct
+    combinations and the class-compressed EM iterates on that count table, whatever the sample size.  Same nIter,
+    1e-9, as for any other input."""
     GL, _ = H.gen_synth.synth(120, 500, 4242)
     opt = H.parse_flags(["--max_kb_dist", "0"] + flags)
     eng, arrays = G.engine_for(GL, opt)
