@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the whole-workload time-to-solution legs")
+    ap.add_argument("--strong-out", default="", help="where the CLI leg writes its TSV (default: /dev/shm if it has room, "
+                                                     "else /dev/null)")
     ap.add_argument("--strict", action="store_true", help="bit-faithful EM kernel instead of the fast one")
     ap.add_argument("--em-path", default="", choices=["", "cell", "warp", "list", "tile"],
                     help="force an EM kernel family (default: the library's choice; 'warp' = dense warp-per-pair kernel)")
@@ -96,6 +99,27 @@ def ref_sample_run(GL, pos, n_sub, threads, tmpdir):
     return n, time.perf_counter() - t0, "port"
 
 
+def ref_sample_mean_passes(GL, pos, n_sub, threads, tmpdir):
+    """Mean EM passes per pair of the reference on the sample (untimed extra run with --extend_out: the nIter column is
+    the 0-based index of the converging pass, 100 = all 100 passes ran without converging)."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        return None
+    g = os.path.join(tmpdir, f"sample_{n_sub}.glf")
+    out = os.path.join(tmpdir, "sample.ld")
+    O.run_ref(["--geno", g, "--probs", "--n_ind", str(GL.shape[1]), "--n_sites", str(n_sub), "--pos", g + ".pos",
+               "--max_kb_dist", "0", "--extend_out"], out, n_threads=threads)
+    tot = n = 0
+    with open(out, "rb") as fh:
+        next(fh)
+        for ln in fh:
+            it = int(ln[ln.rfind(b"\t") + 1:])
+            tot += it + 1 if it < 100 else 100
+            n += 1
+    os.unlink(out)
+    return tot / max(1, n)
+
+
 def pick_sample(GL, pos, threads, target_s, tmpdir):
     """Calibrate on a tiny prefix, then size the sample for ~target_s seconds of CPU wall time."""
     n_sub = 160
@@ -123,6 +147,7 @@ def reference_arm(a):
             n_pairs, dt, kind = ref_sample_run(GL, pos, n_sub, threads, td)
             if k >= a.warmup:
                 times.append(dt)
+        mean_passes = ref_sample_mean_passes(GL, pos, n_sub, threads, td)
     total = sum(times)
     v = n_pairs * len(times) / total
     sample = f"first {n_sub} sites of the workload, all pairs = {n_pairs} pairs per step, --n_threads {threads}"
@@ -130,7 +155,9 @@ def reference_arm(a):
             "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "n_sites": a.n_sites, "n_ind": a.n_ind},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "mean_em_passes_per_pair": mean_passes,
+                             "pair_ind_passes_per_s": v * a.n_ind * mean_passes if mean_passes else None},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -229,6 +256,74 @@ def reduce_over_ranks(values, device, world):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     return mx.tolist(), sm.tolist()
+
+
+def strong_legs(a, eng, P, N, GL, pos, bounds, rank, world, local, barrier, reduce_over_ranks):
+    """Whole-workload time to solution (all n(n-1)/2 pairs once, split over the ranks = GPUs):
+      rows_to_host_sinks  every rank scans its equal-pair-count first-site range through ngsld_scan, rows delivered to a
+                          host sink; wall time between two barriers (= the slowest rank).
+      tsv_cli             the drop-in CLI (ngsld_b200/bin/ngsLD --gpu_n <ranks>) on the same input file, process start to
+                          exit, TSV written to --strong-out (rank 0 runs it; the other ranks wait on the CPU)."""
+    import shutil
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    seen = [0]
+
+    def sink(rows):
+        seen[0] += len(rows)
+    flag = f"/dev/shm/ngsld_bench_{os.environ.get('MASTER_PORT', '0')}_{a.seed}"
+    if rank == 0 and os.path.exists(flag + ".done"):  # left over from a run that died
+        os.unlink(flag + ".done")
+    barrier()
+    t0 = time.perf_counter()
+    eng.scan_sink(P, sink, lo, hi)
+    mine = time.perf_counter() - t0
+    st = eng.stats()
+    barrier()
+    wall = time.perf_counter() - t0
+    mx, sm = reduce_over_ranks([wall, mine, float(seen[0]), st["ms_em"]], "cuda", world)
+    mn = [-x for x in reduce_over_ranks([-mine], "cuda", world)[0]]
+    n_total = a.n_sites * (a.n_sites - 1) // 2
+    out = {"workload": f"all {n_total} pairs of the workload once, {world} GPU(s)",
+           "rows_to_host_sinks": {"seconds": mx[0], "pairs": int(sm[2]), "pairs_per_s": sm[2] / mx[0],
+                                  "slowest_rank_s": mx[1], "fastest_rank_s": mn[0],
+                                  "imbalance": mx[1] / (sm[1] / world), "d2h_bytes": int(sm[2]) * 112,
+                                  "api": "ngsld_scan(row sink) on each rank's ngsld_partition range"}}
+    # ---- the CLI on the same data ----
+    cli = os.path.join(ROOT, "ngsld_b200", "bin", "ngsLD")
+    if rank == 0 and os.path.exists(cli):
+        geno = flag + ".glf"
+        GL.astype("<f8").tofile(geno)
+        with open(geno + ".pos", "w") as fh:
+            fh.write("".join(f"chr1\t{p}\n" for p in pos))
+        target = a.strong_out
+        if not target:
+            target = flag + ".ld" if shutil.disk_usage("/dev/shm").free > 130e9 else "/dev/null"
+        cmd = [cli, "--geno", geno, "--probs", "--n_ind", str(a.n_ind), "--n_sites", str(a.n_sites), "--pos", geno + ".pos",
+               "--max_kb_dist", "0", "--gpu_n", str(world), "--gpu_stats", "--verbose", "0", "--out", target]
+        t1 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        dt = time.perf_counter() - t1
+        size = os.path.getsize(target) if target != "/dev/null" and os.path.exists(target) else None
+        rows = None
+        tl = [l for l in r.stderr.splitlines() if l.startswith("[time]")]
+        wl = [l for l in r.stderr.splitlines() if l.startswith("[writer")]
+        if target != "/dev/null" and os.path.exists(target):
+            os.unlink(target)
+        for f in (geno, geno + ".pos"):
+            os.unlink(f)
+        out["tsv_cli"] = {"seconds": dt, "returncode": r.returncode, "pairs_per_s": n_total / dt if r.returncode == 0 else None,
+                          "out": target if target == "/dev/null" else "/dev/shm (tmpfs)", "tsv_bytes": size,
+                          "time_line": tl[0] if tl else None, "writers": wl,
+                          "command": "ngsLD --geno <600 MB binary GL> --probs --n_ind 500 --n_sites 50000 --pos <pos> "
+                                     f"--max_kb_dist 0 --gpu_n {world} --out <out>: process start to exit"}
+        open(flag + ".done", "w").close()
+    elif os.path.exists(cli):
+        while not os.path.exists(flag + ".done"):  # wait on the CPU: a pending NCCL barrier would occupy SMs
+            time.sleep(0.2)
+    barrier()
+    if rank == 0 and os.path.exists(flag + ".done"):
+        os.unlink(flag + ".done")
+    return out
 
 
 def main():
@@ -368,6 +463,11 @@ def main():
         ms_e2e = f0.elapsed_time(f1)
         e2e = {"pairs": seen[0], "ms": ms_e2e, "h2d": h2d / e_steps, "d2h": d2h / e_steps, "steps": e_steps}
 
+    # ---------------- leg 3: time to solution for the WHOLE workload (strong scaling over the ranks) ----------------
+    strong = None
+    if not a.no_strong:
+        strong = strong_legs(a, eng, P, N, GL, pos, bounds, rank, world, local, barrier, reduce_over_ranks)
+
     # ---------------- reduce over ranks ----------------
     mx, sm = reduce_over_ranks([ms_dev, float(pairs), float(launches), float(passes), ms_em, ms_pearson,
                                 e2e["ms"] if e2e else 0.0, float(e2e["pairs"]) if e2e else 0.0], "cuda", world)
@@ -439,6 +539,8 @@ def main():
             line["e2e"] = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "steps": e2e["steps"],
                            "api": "ngsld_set_sites + ngsld_set_positions + ngsld_scan(row sink) per step"}
+        if strong:
+            line["strong"] = strong
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
             with tempfile.TemporaryDirectory() as td:
