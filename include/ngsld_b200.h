@@ -142,6 +142,15 @@ int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int
  * are kept when the shape is unchanged, so calling it once per batch costs only the copies. */
 int ngsld_set_sites(ngsld_ctx *ctx, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
                     uint64_t n_ind);
+/* Opt-in device-side preparation: takes the FILE's cells (as ngsld_load_geno returns them) and does
+ * what ngsld_prepare_sites + ngsld_set_sites do, with the per-cell math (log / normalise / call_geno / est_maf / exp /
+ * expected genotype; reference read_data.cpp:28-46, gen_func.cpp:886-1009, ngsLD.cpp:107-114) in a kernel on the
+ * uploaded cells.  CUDA's log/exp are not glibc's, so likelihoods and allele frequencies differ from the host path in
+ * the last bits and outputs are no longer bit-identical to the reference (still far inside the 1e-9 contract): the
+ * host path stays the default.  maf_out (may be NULL) receives the allele frequencies. */
+int ngsld_set_sites_raw(ngsld_ctx *ctx, const double *raw, uint64_t n_sites, uint64_t n_ind, int log_scale,
+                        int from_log_cells, int ignore_miss_data, int call_geno, double N_thresh, double call_thresh,
+                        double *maf_out);
 /* replaces params.pos_dist / params.labels (ngsLD.cpp:119-135).  pos_dist NULL = all +inf (no --pos);
  * labels NULL = "(null)" like the reference prints.  labels are only used by ngsld_scan_tsv. */
 int ngsld_set_positions(ngsld_ctx *ctx, const double *pos_dist, const char *const *labels);
@@ -201,6 +210,37 @@ typedef struct {
 /* bins[n_bins] is overwritten; *n_outside (may be NULL) = rows dropped (infinite distance or beyond the last bin). */
 int ngsld_scan_decay(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, double bin_size,
                      uint64_t n_bins, ngsld_decay_bin *bins, uint64_t *n_outside);
+
+/* ---- fused consumer: LD pruning ----------------------------------------------------
+ * The reference's downstream scripts/prune_graph.pl (and prune_ngsLD.py) read the whole TSV back, keep the rows with
+ * dist <= max_dist and weight >= min_weight as edges of a graph (weight = column --field_weight, default 7 = r2; label =
+ * int(weight * 10^4)), and greedily delete the "heaviest" node until no edge is left.  Here the filter runs on the
+ * device right behind the EM, only the surviving edges (a tiny fraction of the pair table) come back to the host, and
+ * ngsld_prune_graph() performs the greedy deletion.  The weight is taken as the scripts see it: the value rounded to the
+ * six decimals the TSV prints, parsed back to double, times 10^precision, truncated. */
+typedef struct {
+  double max_dist;       /* bp; rows with dist > max_dist are no edges (prune_graph.pl: --max_kb_dist * 1000)        */
+  double min_weight;     /* rows with weight < min_weight are no edges                                               */
+  int field;             /* TSV column of the weight: 4 r2_ExpG, 5 D, 6 Dp, 7 r2 (the scripts' --field_weight [7])     */
+  int weight_type;       /* 'a' absolute weight [default], 'e' signed weight, 'n' number of connections             */
+  int weight_precision;  /* decimal digits of the integer edge label [4]                                            */
+  int reserved;
+} ngsld_prune_params;
+typedef struct {
+  uint32_t s1, s2;
+  int32_t label;         /* int(weight * 10^weight_precision), as the scripts compute it                           */
+} ngsld_edge;
+typedef int (*ngsld_edge_sink)(void *user, const ngsld_edge *edges, uint64_t n_edges);
+/* Scan first sites [s1_lo, s1_hi) and deliver only the rows that are edges.  seen (may be NULL) is a host array
+ * [n_sites]: seen[s] is set to 1 for every site that occurs in a row at all (the scripts add both nodes of every line). */
+int ngsld_scan_edges(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p,
+                     const ngsld_prune_params *q, ngsld_edge_sink sink, void *user, uint8_t *seen);
+/* prune_graph.pl's prune_graph_idx on an edge list (host only, no device needed).  labels (may be NULL: site order) break
+ * ties between equally heavy nodes in case-insensitive string order, as the script does.  kept[n_sites]: 1 = in the
+ * pruned set, 0 = excluded, 2 = site occurs in no row; excluded[0 .. *n_excluded) = excluded sites in order of removal
+ * (capacity n_sites; may be NULL). */
+int ngsld_prune_graph(uint64_t n_sites, const char *const *labels, const uint8_t *seen, const ngsld_edge *edges,
+                      uint64_t n_edges, int keep_heavy, uint8_t *kept, uint32_t *excluded, uint64_t *n_excluded);
 
 /* ---- explicit pairs: replaces direct calls of haplo_freq()/pearson_r() (gen_func.hpp:101, ngsLD.hpp:59) */
 int ngsld_pairs(ngsld_ctx *ctx, const uint32_t *s1, const uint32_t *s2, uint64_t n_pairs, int ignore_miss_data,

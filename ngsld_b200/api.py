@@ -55,6 +55,19 @@ class ScanStats(C.Structure):
         return d
 
 
+class PruneParams(C.Structure):
+    """ngsld_prune_params: the edge filter of scripts/prune_graph.pl (--max_kb_dist * 1000, --min_weight, --field_weight,
+    --weight_type, weight precision)."""
+    _fields_ = [("max_dist", C.c_double), ("min_weight", C.c_double), ("field", C.c_int), ("weight_type", C.c_int),
+                ("weight_precision", C.c_int), ("reserved", C.c_int)]
+
+    @classmethod
+    def make(cls, max_dist=float("inf"), min_weight=0.0, field=7, weight_type="a", weight_precision=4):
+        return cls(max_dist, min_weight, field, ord(weight_type), weight_precision, 0)
+
+
+EDGE_DTYPE = np.dtype([("s1", "<u4"), ("s2", "<u4"), ("label", "<i4")])
+EDGE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 ROW_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64)
 
@@ -90,6 +103,7 @@ def load_library():
         "ngsld_set_chunk_rows": (i32, [vp, u64]),
         "ngsld_prepare_sites": (i32, [pd, u64, u64, i32, i32, i32, i32, dbl, dbl, i32, pd, pd, pd]),
         "ngsld_set_sites": (i32, [vp, pd, pd, pd, u64, u64]),
+        "ngsld_set_sites_raw": (i32, [vp, pd, u64, u64, i32, i32, i32, i32, dbl, dbl, vp]),
         "ngsld_set_positions": (i32, [vp, vp, vp]),
         "ngsld_scan_defaults": (None, [C.POINTER(ScanParams)]),
         "ngsld_scan_count": (i32, [vp, u64, u64, C.POINTER(ScanParams), C.POINTER(u64)]),
@@ -106,6 +120,8 @@ def load_library():
         "ngsld_get_stats": (i32, [vp, C.POINTER(ScanStats)]),
         "ngsld_scan_decay": (i32, [vp, u64, u64, C.POINTER(ScanParams), dbl, u64, vp, C.POINTER(u64)]),
         "ngsld_pairs": (i32, [vp, pu32, pu32, u64, i32, i32, vp]),
+        "ngsld_scan_edges": (i32, [vp, u64, u64, C.POINTER(ScanParams), C.POINTER(PruneParams), EDGE_SINK, vp, vp]),
+        "ngsld_prune_graph": (i32, [u64, vp, vp, vp, u64, i32, vp, vp, C.POINTER(u64)]),
         "ngsld_site_seeds": (i32, [u64, u64, pu64]),
         "ngsld_plan_count": (i32, [pd, vp, u64, C.POINTER(ScanParams), u64, u64, C.POINTER(u64)]),
         "ngsld_plan_partition": (i32, [pd, vp, u64, C.POINTER(ScanParams), i32, pu64]),
@@ -129,7 +145,7 @@ EXPORTED = ["ngsld_abi_version", "ngsld_device_count", "ngsld_create", "ngsld_de
             "ngsld_scan_tsv", "ngsld_scan_device", "ngsld_get_stats", "ngsld_pairs", "ngsld_site_seeds",
             "ngsld_tsv_header", "ngsld_probe_fp64", "ngsld_plan_count", "ngsld_plan_partition", "ngsld_load_geno",
             "ngsld_load_positions", "ngsld_free", "ngsld_scan_decay", "ngsld_scan_tsv_into", "ngsld_tsv_row_bound",
-            "ngsld_alloc_host", "ngsld_free_host", "ngsld_share_sites"]
+            "ngsld_alloc_host", "ngsld_free_host", "ngsld_share_sites", "ngsld_set_sites_raw", "ngsld_scan_edges", "ngsld_prune_graph"]
 
 
 def prepare_sites(raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,
@@ -194,6 +210,25 @@ def read_positions(path, n_sites, header=False):
     L.ngsld_free(blob)
     labels = [x.decode() for x in raw.split(b"\0")[:n_sites]]
     return labels, dist
+
+
+def prune_graph(n_sites, labels, seen, edges, keep_heavy=False):
+    """ngsld_prune_graph (host only): (kept [n_sites] uint8: 1 kept / 0 excluded / 2 in no row, excluded sites in order)."""
+    seen = np.ascontiguousarray(seen, np.uint8)
+    edges = np.ascontiguousarray(edges, EDGE_DTYPE)
+    kept = np.zeros(n_sites, np.uint8)
+    excl = np.zeros(n_sites, np.uint32)
+    n_ex = C.c_uint64(0)
+    lab_ptr = None
+    if labels is not None:
+        arr = (C.c_char_p * n_sites)(*[l.encode() if isinstance(l, str) else l for l in labels])
+        lab_ptr = C.cast(arr, C.c_void_p)
+    rc = load_library().ngsld_prune_graph(n_sites, lab_ptr, seen.ctypes.data_as(C.c_void_p), edges.ctypes.data_as(C.c_void_p),
+                                          len(edges), int(keep_heavy), kept.ctypes.data_as(C.c_void_p),
+                                          excl.ctypes.data_as(C.c_void_p), C.byref(n_ex))
+    if rc != 0:
+        raise NgsldError(rc, "invalid pruning input")
+    return kept, excl[:n_ex.value].copy()
 
 
 def plan_count(maf, pos_dist, params, s1_lo=0, s1_hi=None):
@@ -273,6 +308,20 @@ class Engine:
         assert gl.shape == (n_sites, n_ind, 3) and maf.shape == (n_sites,)
         self._check(self._lib.ngsld_set_sites(self._h, gl, expg, maf, n_sites, n_ind))
         self.n_sites, self.n_ind = n_sites, n_ind
+
+    def set_sites_raw(self, raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,
+                      N_thresh=0.0, call_thresh=0.0):
+        """ngsld_set_sites_raw: file cells -> device, prepared there (opt-in; not bit-identical to the host path).
+        Returns the allele frequencies."""
+        raw = np.ascontiguousarray(raw, np.float64)
+        n_sites, n_ind, three = raw.shape
+        assert three == 3
+        maf = np.empty(n_sites)
+        self._check(self._lib.ngsld_set_sites_raw(self._h, raw, n_sites, n_ind, int(log_scale), int(from_log_cells),
+                                                  int(ignore_miss_data), int(call_geno), N_thresh, call_thresh,
+                                                  maf.ctypes.data_as(C.c_void_p)))
+        self.n_sites, self.n_ind = n_sites, n_ind
+        return maf
 
     def set_positions(self, pos_dist=None, labels=None):
         pd_ptr = None
@@ -364,6 +413,21 @@ class Engine:
         """ngsld_share_sites: take over the site table of another Engine (another GPU) by device-to-device copy."""
         self._check(self._lib.ngsld_share_sites(self._h, other._h))
         self.n_sites, self.n_ind = other.n_sites, other.n_ind
+
+    def scan_edges(self, params, prune, s1_lo=0, s1_hi=None):
+        """ngsld_scan_edges: (edges as EDGE_DTYPE array in (s1, s2) order, seen [n_sites] uint8)."""
+        hi = self.n_sites if s1_hi is None else s1_hi
+        parts = []
+
+        def _cb(user, ptr, n):
+            buf = (C.c_char * (n * EDGE_DTYPE.itemsize)).from_address(ptr)
+            parts.append(np.frombuffer(buf, EDGE_DTYPE, count=n).copy())
+            return 0
+        cb = EDGE_SINK(_cb)
+        seen = np.zeros(self.n_sites, np.uint8)
+        self._check(self._lib.ngsld_scan_edges(self._h, s1_lo, hi, C.byref(params), C.byref(prune), cb, None,
+                                               seen.ctypes.data_as(C.c_void_p)))
+        return (np.concatenate(parts) if parts else np.zeros(0, EDGE_DTYPE)), seen
 
     def scan_device(self, params, s1_lo=0, s1_hi=None):
         hi = self.n_sites if s1_hi is None else s1_hi

@@ -1,6 +1,7 @@
 // Everything on the path that is not the fast EM: the bit-faithful EM, the x87-exact r2_ExpG,
 // window -> pair-list expansion, per-site taus sampling, and an FP64 issue-rate probe.
 #include "aux_kernels.cuh"
+#include "fixed6.cuh"
 #include "fp80.cuh"
 #include "pearson.cuh"
 
@@ -268,6 +269,137 @@ __global__ void __launch_bounds__(256) decay_bins_kernel(const ngsld_pair_row *r
         atomicAdd((unsigned long long *)&bins[bin].n[j], (unsigned long long)tc);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LD pruning, device half (ngsld_scan_edges): the row filter of the reference's scripts/prune_graph.pl:118-137 applied
+// right behind the EM.  The weight is what the script parses from the TSV: the value rounded to six decimals
+// (fmt::fixed6, exactly as "%f" prints it) read back as a double.  Rows that pass are appended to `edges` (the lanes of
+// a warp reserve their slots with one atomic); every site that occurs in a row is flagged in `seen`.
+__global__ void __launch_bounds__(256) prune_edges_kernel(const ngsld_pair_row *rows, unsigned long long n, ngsld_prune_params q,
+                                                          double precision, ngsld_edge *edges, unsigned long long *n_edges,
+                                                          unsigned char *seen) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long n_round = (n + 31ull) & ~31ull;
+  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n_round; p += stride) {
+    bool edge = false;
+    ngsld_edge e;
+    e.s1 = e.s2 = 0;
+    e.label = 0;
+    if (p < n) {
+      const ngsld_pair_row r = rows[p];
+      seen[r.s1] = 1;
+      seen[r.s2] = 1;
+      const double x = q.field == 4 ? r.r2_expg : q.field == 5 ? r.D : q.field == 6 ? r.Dp : r.r2;
+      if (isfinite(x) && isfinite(r.dist) && !(r.dist > q.max_dist)) {
+        unsigned long long N;
+        double w = fmt::fixed6(x, N) ? __ddiv_rn((double)N, 1000000.0) : fabs(x);  // the printed decimal, parsed back
+        if (x < 0) w = -w;
+        if (q.weight_type == 'a') w = fabs(w);
+        if (!(w < q.min_weight)) {
+          if (q.weight_type == 'n') w = 1.0;
+          edge = true;
+          e.s1 = r.s1;
+          e.s2 = r.s2;
+          e.label = (int32_t)__dmul_rn(w, precision);  // int(): truncation towards zero
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, edge);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(n_edges, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (edge) edges[base + __popc(m & ((1u << lane) - 1u))] = e;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0 (opt-in): the per-cell preparation of the reference on the device -- read_geno()'s log +
+// normalisation (shared/read_data.cpp:28-46 with conv_space / post_prob / logsum, gen_func.cpp:123-151, 920-932), the
+// optional call_geno() pass (gen_func.cpp:886-914), est_maf() (gen_func.cpp:974-1009) and the exp + expected-genotype
+// loop of main (ngsLD.cpp:107-114).  One warp per site, in place on the uploaded file cells.  CUDA's log/exp are not
+// glibc's: likelihoods differ from the host path by a few ulp (and the allele frequency, summed as a tree instead of
+// in individual order, by ~sqrt(n_ind) ulp), so results are NOT bit-identical to the reference with this path; the
+// default stays ngsld_prepare_sites on the host.
+__device__ __forceinline__ double log_norm3_dev(double a, double b, double c) {  // logsum(), gen_func.cpp:135-151
+  double top = a;
+  if (b >= top) top = b;
+  if (c >= top) top = c;
+  if (top == -INFINITY) return -INFINITY;
+  double s = 0;
+  s += exp(a - top);
+  s += exp(b - top);
+  s += exp(c - top);
+  return log(s) + top;
+}
+
+__global__ void __launch_bounds__(128) prep_sites_kernel(double *gl, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad, int to_log,
+                                                         int ignore_miss, int call_geno, double n_thresh, double call_thresh,
+                                                         double *expg, double *maf, int *nan_flag) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const double big = 1e15;
+  for (uint32_t s = warp; s < n_sites; s += n_warps) {
+    double *row = gl + (size_t)s * n_pad * 3;
+    double num = 0, den = 0;
+    for (uint32_t i = lane; i < n_ind; i += 32) {
+      double v[3];
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        double x = row[3 * (size_t)i + g];
+        if (to_log) {  // conv_space(log)
+          x = log(x);
+          if (x == -INFINITY) x = -big;
+        }
+        v[g] = x;
+      }
+      const double z = log_norm3_dev(v[0], v[1], v[2]);  // post_prob()
+      v[0] -= z; v[1] -= z; v[2] -= z;
+      if (v[0] != v[0] || v[1] != v[1] || v[2] != v[2]) *nan_flag = 1;  // read_data.cpp:42-45
+      if (call_geno) {  // call_geno(geno, 3, log_scale = true, N_thresh, call_thresh, 0)
+        int imax = 0, imin = 0;
+        double vmax = -INFINITY, vmin = INFINITY;
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          if (v[g] > vmax) { vmax = v[g]; imax = g; }
+          if (v[g] < vmin) { vmin = v[g]; imin = g; }
+        }
+        double best = exp(v[imax]);
+        if (v[imin] == v[imax]) best = -1;
+        if (best < n_thresh) v[0] = v[1] = v[2] = log(1.0 / 3.0);
+        if (best >= call_thresh) {
+          v[0] = v[1] = v[2] = -big;
+          v[imax] = 0.0;
+        }
+      }
+      // est_maf(): posterior under the uniform prior, accumulated over the individuals
+      double a = v[0] - v[1], b = v[1] - v[2];
+      if (!(a >= 0)) a = -a;
+      if (!(b >= 0)) b = -b;
+      const bool flat = a < NGSLD_EPS && b < NGSLD_EPS;
+      if (!(flat && ignore_miss)) {
+        const double z2 = log_norm3_dev(v[0], v[1], v[2]);
+        const double p0 = exp(v[0] - z2), p1 = exp(v[1] - z2), p2 = exp(v[2] - z2);
+        num += p1 + p2 * 2.0;
+        den += 2.0 * p1 + (p0 + p2) * 2.0;
+      }
+      // normal space + expected genotype (ngsLD.cpp:107-114)
+      const double e0 = exp(v[0]), e1 = exp(v[1]), e2 = exp(v[2]);
+      row[3 * (size_t)i] = e0;
+      row[3 * (size_t)i + 1] = e1;
+      row[3 * (size_t)i + 2] = e2;
+      expg[(size_t)s * n_ind + i] = e1 + 2.0 * e2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
+    if (lane == 0) maf[s] = num / den;
   }
 }
 

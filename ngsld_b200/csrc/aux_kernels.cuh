@@ -17,5 +17,9 @@ __global__ void taus_sample_kernel(const unsigned long long *site_seeds, const u
                                    uint32_t *s2);
 __global__ void decay_bins_kernel(const ngsld_pair_row *rows, unsigned long long n, double bin_size,
                                   unsigned long long n_bins, ngsld_decay_bin *bins, unsigned long long *outside);
+__global__ void prune_edges_kernel(const ngsld_pair_row *rows, unsigned long long n, ngsld_prune_params q, double precision,
+                                   ngsld_edge *edges, unsigned long long *n_edges, unsigned char *seen);
+__global__ void prep_sites_kernel(double *gl, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad, int to_log, int ignore_miss,
+                                  int call_geno, double n_thresh, double call_thresh, double *expg, double *maf, int *nan_flag);
 __global__ void fp64_probe_kernel(double *out, int iters);
 }  // namespace aux

@@ -13,6 +13,13 @@
 //   --gpu_n INT       GPUs to use (default: all visible)
 //   --gpu_strict      bit-faithful EM kernel (hap/D/D'/r2 bit-identical to the reference; slower)
 //   --gpu_stats       print pairs, EM passes and device times per GPU to stderr
+//   --gpu_prune FILE  LD pruning fused behind the scan (what scripts/prune_graph.pl does with the TSV): no TSV is written;
+//                     FILE receives the labels of the unlinked sites that remain, one per line, in site order.  Edge filter
+//                     and options as in the script: --gpu_prune_max_kb_dist KB [inf], --gpu_prune_min_weight W [0],
+//                     --gpu_prune_field 4|5|6|7 [7 = r2], --gpu_prune_weight_type a|e|n [a], --gpu_prune_keep_heavy,
+//                     --gpu_prune_excl FILE (excluded sites in order of removal)
+//   --gpu_prep        per-site preparation (log / normalise / maf / expected genotypes) on the GPU instead of the host:
+//                     faster on very large inputs, last-bit differences from the reference (CUDA log/exp are not glibc's)
 #include <errno.h>
 #include <fcntl.h>
 #include <getopt.h>
@@ -77,7 +84,11 @@ struct Options {
   const char *out = nullptr;
   int n_threads = 1, verbose = 1;
   int gpu_n = 0;
-  bool gpu_strict = false, gpu_stats = false;
+  bool gpu_strict = false, gpu_stats = false, gpu_prep = false;
+  const char *prune_out = nullptr, *prune_excl = nullptr;
+  double prune_max_kb = INFINITY, prune_min_weight = 0;
+  int prune_field = 7, prune_type = 'a';
+  bool prune_keep_heavy = false;
 };
 
 static void parse(Options &o, int argc, char **argv) {
@@ -106,6 +117,14 @@ static void parse(Options &o, int argc, char **argv) {
                                   {"gpu_n", required_argument, NULL, 1001},
                                   {"gpu_strict", no_argument, NULL, 1002},
                                   {"gpu_stats", no_argument, NULL, 1003},
+                                  {"gpu_prep", no_argument, NULL, 1004},
+                                  {"gpu_prune", required_argument, NULL, 1010},
+                                  {"gpu_prune_max_kb_dist", required_argument, NULL, 1011},
+                                  {"gpu_prune_min_weight", required_argument, NULL, 1012},
+                                  {"gpu_prune_field", required_argument, NULL, 1013},
+                                  {"gpu_prune_weight_type", required_argument, NULL, 1014},
+                                  {"gpu_prune_keep_heavy", no_argument, NULL, 1015},
+                                  {"gpu_prune_excl", required_argument, NULL, 1016},
                                   {0, 0, 0, 0}};
   int c;
   while ((c = getopt_long_only(argc, argv, "g:pln:s:Z:d:D:f:mcN:C:r:S:xo:t:V:", table, NULL)) != -1) switch (c) {
@@ -132,6 +151,14 @@ static void parse(Options &o, int argc, char **argv) {
       case 1001: o.gpu_n = atoi(optarg); break;
       case 1002: o.gpu_strict = true; break;
       case 1003: o.gpu_stats = true; break;
+      case 1004: o.gpu_prep = true; break;
+      case 1010: o.prune_out = optarg; break;
+      case 1011: o.prune_max_kb = atof(optarg); break;
+      case 1012: o.prune_min_weight = atof(optarg); break;
+      case 1013: o.prune_field = atoi(optarg); break;
+      case 1014: o.prune_type = optarg[0]; break;
+      case 1015: o.prune_keep_heavy = true; break;
+      case 1016: o.prune_excl = optarg; break;
       default: exit(-1);
     }
   if (o.verbose >= 1) {
@@ -179,8 +206,9 @@ int main(int argc, char **argv) {
   // Here rows arrive as finished text in page-locked slab buffers, so the file is a plain descriptor: a regular file is
   // written with pwrite() by several writer threads at offsets that are known as soon as all earlier slabs have been
   // formatted; a pipe / terminal / device gets the slabs in order from one writer.
+  const bool prune_mode = o.prune_out != nullptr;
   int out_fd = STDOUT_FILENO;
-  if (o.out) out_fd = open(o.out, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (o.out && !prune_mode) out_fd = open(o.out, O_WRONLY | O_CREAT | O_TRUNC, 0666);
   if (out_fd < 0) die(fn, "cannot open output file!");
   struct stat ost;
   const bool seekable = fstat(out_fd, &ost) == 0 && S_ISREG(ost.st_mode);
@@ -199,7 +227,7 @@ int main(int argc, char **argv) {
   };
   char header[512];
   const int hl = ngsld_tsv_header(o.extend_out, header, sizeof header);
-  if (!write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
+  if (!prune_mode && !write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
 
   const double t_start = wall_s();
   if (o.verbose >= 1) fprintf(stderr, "> Reading data from file...\n");
@@ -212,13 +240,17 @@ int main(int argc, char **argv) {
   if (o.verbose >= 1) fprintf(stderr, "==> Calculating MAF for all sites...\n");
   // prepared in place: the normalised likelihoods overwrite the file's cells (one genotype matrix in host memory, like
   // the reference, instead of two)
-  std::vector<double> expg((size_t)o.n_sites * o.n_ind), maf(o.n_sites);
+  std::vector<double> expg, maf(o.n_sites);
   const int host_threads = std::max(o.n_threads, (int)std::thread::hardware_concurrency());
-  int rc = ngsld_prepare_sites(cells.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data,
-                               o.call_geno, o.N_thresh, o.call_thresh, host_threads, cells.data(), expg.data(), maf.data());
-  if (rc == NGSLD_E_DATA) die("read_geno", "NaN found! Is the file format correct?");
-  if (rc == NGSLD_E_INVALID && o.call_geno && o.N_thresh > o.call_thresh)  // raised by call_geno() in the reference: after the read
+  int rc = NGSLD_OK;
+  if (o.call_geno && o.N_thresh > o.call_thresh)  // raised by call_geno() in the reference: after the read
     die("call_geno", "missing data threshold must be smaller than calling genotype threshold!");
+  if (!o.gpu_prep) {
+    expg.resize((size_t)o.n_sites * o.n_ind);
+    rc = ngsld_prepare_sites(cells.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data, o.call_geno,
+                             o.N_thresh, o.call_thresh, host_threads, cells.data(), expg.data(), maf.data());
+  }
+  if (rc == NGSLD_E_DATA) die("read_geno", "NaN found! Is the file format correct?");
   if (rc != NGSLD_OK) die(fn, "site preparation failed!");
   const std::vector<double> &gl = cells;
   const double t_prep = wall_s();
@@ -261,7 +293,11 @@ int main(int argc, char **argv) {
   auto from_host = [&](int g) -> int {
     int r = ngsld_create(&ctx[g], g);
     if (r) return r;
-    r = ngsld_set_sites(ctx[g], gl.data(), expg.data(), maf.data(), o.n_sites, o.n_ind);
+    if (o.gpu_prep)
+      r = ngsld_set_sites_raw(ctx[g], cells.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data, o.call_geno,
+                              o.N_thresh, o.call_thresh, NULL);
+    else
+      r = ngsld_set_sites(ctx[g], gl.data(), expg.data(), maf.data(), o.n_sites, o.n_ind);
     if (r) return r;
     return ngsld_set_positions(ctx[g], o.in_pos ? pos_dist.data() : nullptr, o.in_pos ? label_ptr.data() : nullptr);
   };
@@ -269,6 +305,7 @@ int main(int argc, char **argv) {
     for (int g = 0; g < n_gpu; g++)
       if (rcs[g]) {
         fprintf(stderr, "GPU %d: %s\n", g, ngsld_last_error(ctx[g]));
+        if (rcs[g] == NGSLD_E_DATA && strstr(ngsld_last_error(ctx[g]), "NaN found")) die("read_geno", "NaN found! Is the file format correct?");
         die(fn, rcs[g] == NGSLD_E_DATA ? "invalid allele frequencies" : "failed to initialise the GPU engine!");
       }
   };
@@ -296,6 +333,102 @@ int main(int argc, char **argv) {
   }
   const double t_upload = wall_s();
 
+  if (prune_mode) {
+    // ---- LD pruning: every GPU filters the rows of its slabs into edges on the device; the host prunes the graph ----
+    ngsld_prune_params Q;
+    memset(&Q, 0, sizeof Q);
+    Q.max_dist = o.prune_max_kb * 1000.0;
+    Q.min_weight = o.prune_min_weight;
+    Q.field = o.prune_field;
+    Q.weight_type = o.prune_type;
+    Q.weight_precision = 4;
+    const int n_parts = n_gpu * 8;
+    std::vector<uint64_t> pb(n_parts + 1);
+    if (ngsld_partition(ctx[0], &P, n_parts, pb.data()) != NGSLD_OK) die(fn, "failed to partition the pair space!");
+    std::vector<std::vector<ngsld_edge>> part_edges(n_parts);
+    std::vector<std::vector<uint8_t>> seen(n_gpu, std::vector<uint8_t>(o.n_sites, 0));
+    std::vector<int> prc(n_gpu, 0);
+    std::vector<uint64_t> rows_g(n_gpu, 0);
+    std::mutex pm;
+    int next_part = 0;
+    auto edge_sink = [](void *user, const ngsld_edge *e, uint64_t n) -> int {
+      auto *v = (std::vector<ngsld_edge> *)user;
+      v->insert(v->end(), e, e + n);
+      return 0;
+    };
+    const double tp0 = wall_s();
+    {
+      std::vector<std::thread> th;
+      for (int g = 0; g < n_gpu; g++)
+        th.emplace_back([&, g]() {
+          for (;;) {
+            int k;
+            {
+              std::lock_guard<std::mutex> lk(pm);
+              if (next_part >= n_parts) return;
+              k = next_part++;
+            }
+            prc[g] = ngsld_scan_edges(ctx[g], pb[k], pb[k + 1], &P, &Q, edge_sink, &part_edges[k], seen[g].data());
+            if (prc[g]) return;
+            ngsld_scan_stats st;
+            ngsld_get_stats(ctx[g], &st);
+            rows_g[g] += st.n_pairs;
+          }
+        });
+      for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < n_gpu; g++)
+      if (prc[g]) {
+        fprintf(stderr, "GPU %d: %s\n", g, ngsld_last_error(ctx[g]));
+        die(fn, "pair scan failed!");
+      }
+    const double tp1 = wall_s();
+    std::vector<ngsld_edge> edges;
+    for (auto &v : part_edges) edges.insert(edges.end(), v.begin(), v.end());
+    for (int g = 1; g < n_gpu; g++)
+      for (uint64_t s = 0; s < o.n_sites; s++) seen[0][s] |= seen[g][s];
+    std::vector<uint8_t> kept(o.n_sites);
+    std::vector<uint32_t> excl(o.n_sites);
+    uint64_t n_excl = 0;
+    if (ngsld_prune_graph(o.n_sites, o.in_pos ? label_ptr.data() : nullptr, seen[0].data(), edges.data(), edges.size(),
+                          o.prune_keep_heavy, kept.data(), excl.data(), &n_excl) != NGSLD_OK)
+      die(fn, "graph pruning failed!");
+    const double tp2 = wall_s();
+    auto site_name = [&](uint64_t s, char *tmp) -> const char * {
+      if (o.in_pos) return label_ptr[s];
+      snprintf(tmp, 32, "%lu", (unsigned long)s);
+      return tmp;
+    };
+    FILE *pf = strcmp(o.prune_out, "-") ? fopen(o.prune_out, "w") : stdout;
+    if (!pf) die(fn, "cannot open output file!");
+    uint64_t n_kept = 0, n_nodes = 0;
+    char tmp[32];
+    for (uint64_t s = 0; s < o.n_sites; s++) {
+      if (kept[s] != 2) n_nodes++;
+      if (kept[s] == 1) {
+        fprintf(pf, "%s\n", site_name(s, tmp));
+        n_kept++;
+      }
+    }
+    if (pf != stdout) fclose(pf);
+    if (o.prune_excl) {
+      FILE *ef = fopen(o.prune_excl, "w");
+      if (!ef) die(fn, "cannot open output file!");
+      for (uint64_t k = 0; k < n_excl; k++) fprintf(ef, "%s\n", site_name(excl[k], tmp));
+      fclose(ef);
+    }
+    if (o.gpu_stats) {
+      uint64_t rows = 0;
+      for (auto r : rows_g) rows += r;
+      fprintf(stderr, "[prune] %lu rows scanned on %d GPU(s) in %.2f s, %lu edges (%.4f %% of the rows) between %lu sites came back to the host, pruning %.2f s: %lu sites kept, %lu excluded\n",
+              rows, n_gpu, tp1 - tp0, edges.size(), rows ? 100.0 * edges.size() / rows : 0.0, n_nodes, tp2 - tp1, n_kept, n_excl);
+    }
+    for (auto c : ctx) ngsld_destroy(c);
+    ngsld_free(label_blob);
+    if (o.verbose >= 1) fprintf(stderr, "Done!\n");
+    return 0;
+  }
+
   // ---- work units: slabs of first sites with (about) the same number of rows, taken in order by the GPU threads ----
   uint64_t total_rows = 0;
   if (ngsld_scan_count(ctx[0], 0, o.n_sites, &P, &total_rows) != NGSLD_OK) {
@@ -303,7 +436,7 @@ int main(int argc, char **argv) {
     die(fn, "failed to plan the pair scan!");
   }
   const uint64_t row_bound = ngsld_tsv_row_bound(ctx[0], o.extend_out);
-  uint64_t buf_bytes = 1ull << 30;  // per slab buffer; a scan drains its chunk pipeline at the end, so slabs stay long
+  uint64_t buf_bytes = 512ull << 20;  // per slab buffer; a scan drains its chunk pipeline at the end, so slabs stay long
   if (const char *e = getenv("NGSLD_CLI_BUF_MB"))
     if (atoll(e) > 0) buf_bytes = (uint64_t)atoll(e) << 20;
   uint64_t rows_per_slab = std::max<uint64_t>(1, std::min<uint64_t>(16ull << 20, buf_bytes / row_bound));
@@ -320,23 +453,32 @@ int main(int argc, char **argv) {
   const uint64_t cap = std::max<uint64_t>(slab_rows_max * row_bound, 4096);
 
   if (o.verbose >= 1) fprintf(stderr, "==> Waiting for all threads to finish...\n");
-  const int n_writers = seekable ? std::max(1, std::min(n_gpu, 8)) : 1;
+  // one pwrite() stream into the page cache moves ~3.5 GB/s; a GPU produces ~4 GB/s of text
+  const int n_writers = seekable ? std::max(2, std::min(2 * n_gpu, 16)) : 1;
   const int n_bufs = n_gpu + n_writers + 1;
   struct Buf {
     char *p = nullptr;
     bool pinned = false;
   };
   std::vector<Buf> bufs(n_bufs);
-  for (auto &b : bufs) {
-    void *q = nullptr;
-    if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
-      b.p = (char *)q;
-      b.pinned = true;
-    } else {
-      b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
-    }
-    if (!b.p) die(fn, "cannot allocate the output buffers!");
+  const double t_alloc0 = wall_s();
+  {
+    std::vector<std::thread> th;  // page-locking is kernel work per page: in parallel
+    for (auto &b : bufs)
+      th.emplace_back([&b, cap]() {
+        void *q = nullptr;
+        if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
+          b.p = (char *)q;
+          b.pinned = true;
+        } else {
+          b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
+        }
+      });
+    for (auto &t : th) t.join();
   }
+  for (auto &b : bufs)
+    if (!b.p) die(fn, "cannot allocate the output buffers!");
+  const double t_alloc = wall_s() - t_alloc0;
   struct Slab {
     int buf = -1;
     uint64_t bytes = 0, rows = 0;
@@ -492,10 +634,10 @@ int main(int argc, char **argv) {
     for (int w = 0; w < n_writers; w++)
       fprintf(stderr, "[writer %d] %.2f GB in %.2f s of %s = %.2f GB/s\n", w, wacc[w].bytes / 1e9, wacc[w].s_write,
               seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
-    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s)\n",
+    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, allocated in %.2f s)\n",
             t_read - t_start, t_prep - t_read, n_gpu, t_upload - t_prep, host_upload_all || n_gpu == 1 ? "from the host" : "one upload, then GPU to GPU",
             t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - hl) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
-            bufs[0].pinned ? "page-locked" : "pageable");
+            bufs[0].pinned ? "page-locked" : "pageable", t_alloc);
   }
   if (o.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   for (auto c : ctx) ngsld_destroy(c);

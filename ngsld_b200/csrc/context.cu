@@ -18,6 +18,7 @@
 #include "format.cuh"
 #include "host/host_prep.h"
 #include "host/loader.h"
+#include "host/prune.h"
 
 namespace emfast {
 #define DECL_LPG(n)                              \
@@ -44,6 +45,8 @@ double now_ms() {
 struct ChunkBuf {
   uint32_t *d_s1 = nullptr, *d_s2 = nullptr;
   uint32_t *d_resid = nullptr;       // pairs of the chunk the cell kernel left to the dense kernel
+  ngsld_edge *d_edges = nullptr;     // rows of the chunk that are graph edges (ngsld_scan_edges), + their number
+  unsigned long long *d_n_edges = nullptr;
   ngsld_pair_row *d_rows = nullptr;
   ngsld_pair_row *h_rows = nullptr;  // pinned
   char *d_text = nullptr;            // formatted TSV bytes (slots, then compacted)
@@ -110,6 +113,13 @@ struct ngsld_ctx {
   uint2 *d_tiles = nullptr;
   size_t cap_compact = 0, cap_tiles = 0;
   DevCounters *d_ctr = nullptr;
+  // LD pruning (ngsld_scan_edges): when active, every chunk's rows are filtered into an edge list on the device
+  bool prune_active = false;
+  ngsld_prune_params prune_q;
+  unsigned char *d_seen = nullptr;
+  ngsld_edge_sink edge_sink = nullptr;
+  void *edge_user = nullptr;
+  std::vector<ngsld_edge> h_edges;
   // LD-decay bins (ngsld_scan_decay): when active, every chunk is folded into them on the device
   bool decay_active = false;
   double decay_bin_size = 0;
@@ -153,6 +163,8 @@ void free_chunks(ngsld_ctx *c) {
     dfree(b.d_s1);
     dfree(b.d_s2);
     dfree(b.d_resid);
+    dfree(b.d_edges);
+    dfree(b.d_n_edges);
     dfree(b.d_rows);
     dfree(b.d_text);
     dfree(b.d_text_out);
@@ -772,6 +784,18 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
                                                      c->d_decay_outside);
     c->stats.n_launches++;
   }
+  if (c->prune_active) {
+    if (!b.d_edges) {
+      CUDA_TRY(c, cudaMalloc(&b.d_edges, c->alloc_rows * sizeof(ngsld_edge)));
+      CUDA_TRY(c, cudaMalloc(&b.d_n_edges, sizeof(unsigned long long)));
+    }
+    CUDA_TRY(c, cudaMemsetAsync(b.d_n_edges, 0, sizeof(unsigned long long), c->s_main));
+    const unsigned pb = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 8);
+    double prec = 1;
+    for (int k = 0; k < c->prune_q.weight_precision; k++) prec *= 10;
+    aux::prune_edges_kernel<<<pb, 256, 0, c->s_main>>>(b.d_rows, n, c->prune_q, prec, b.d_edges, b.d_n_edges, c->d_seen);
+    c->stats.n_launches++;
+  }
   if (mode == MODE_TEXT) {
     CUDA_TRY(c, cudaEventRecord(b.ev_f0, c->s_main));
     int rc = fmt::launch_format(*fa, T, b.d_rows, n, b.d_text, b.d_line_off, b.d_text_out, c->sm_count, c->s_main);
@@ -855,6 +879,21 @@ int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
     if (d.text && d.text(d.user, b.h_text, bytes, b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "text sink aborted the scan");
   } else if (d.mode == MODE_ROWS) {
     if (d.rows && d.rows(d.user, b.h_rows, b.n_rows) != 0) return fail(c, NGSLD_E_SINK, "row sink aborted the scan");
+  }
+  if (c->prune_active) {
+    unsigned long long ne = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&ne, b.d_n_edges, sizeof ne, cudaMemcpyDeviceToHost, c->s_copy));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+    c->h_edges.resize(ne);
+    if (ne) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->h_edges.data(), b.d_edges, ne * sizeof(ngsld_edge), cudaMemcpyDeviceToHost, c->s_copy));
+      CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+      // the lanes of different warps append concurrently: restore (s1, s2) order inside the chunk
+      std::sort(c->h_edges.begin(), c->h_edges.end(),
+                [](const ngsld_edge &x, const ngsld_edge &y) { return x.s1 != y.s1 ? x.s1 < y.s1 : x.s2 < y.s2; });
+      c->stats.d2h_bytes += ne * sizeof(ngsld_edge) + 8;
+      if (c->edge_sink && c->edge_sink(c->edge_user, c->h_edges.data(), ne) != 0) return fail(c, NGSLD_E_SINK, "edge sink aborted the scan");
+    }
   }
   return NGSLD_OK;
 }
@@ -1065,6 +1104,7 @@ void ngsld_destroy(ngsld_ctx *c) {
   dfree(c->d_ctr);
   dfree(c->d_decay_bins);
   dfree(c->d_decay_outside);
+  dfree(c->d_seen);
   for (auto &b : c->buf) {
     cudaEvent_t evs[] = {b.ev_ready, b.ev_em0, b.ev_em1, b.ev_p0, b.ev_p1, b.ev_f0, b.ev_f1, b.ev_done};
     for (auto ev : evs)
@@ -1108,22 +1148,18 @@ int ngsld_prepare_sites(const double *raw, uint64_t n_sites, uint64_t n_ind, int
   return hostprep::prepare_sites(raw, n_sites, n_ind, o, n_threads, gl, expg, maf) == 0 ? NGSLD_OK : NGSLD_E_DATA;
 }
 
-int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
-                    uint64_t n_ind) {
-  if (!c) return NGSLD_E_INVALID;
-  if (!gl || !expg || !maf || n_sites == 0 || n_ind == 0) return fail(c, NGSLD_E_INVALID, "null or empty site arrays");
+namespace {
+// Common head of ngsld_set_sites / ngsld_set_sites_raw: device buffers for the shape, positions and labels dropped.
+int begin_sites(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind) {
   if (n_sites >= (1ull << 32) - 1) return fail(c, NGSLD_E_INVALID, "n_sites must be below 2^32-1");
-  for (uint64_t s = 0; s < n_sites; s++)
-    if (maf[s] < 0 || maf[s] > 1) return fail(c, NGSLD_E_DATA, "invalid allele frequencies");  // gen_func.cpp:1030
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   dfree(c->d_cum);
   dfree(c->d_label_blob);
   dfree(c->d_label_off);
   c->have_pos = c->have_labels = false;
-  const uint64_t n_pad = (n_ind + 1) & ~1ull;  // rows stay 16-byte aligned for the TMA bulk copies
+  const uint64_t n_pad = (n_ind + 1) & ~1ull;    // rows stay 16-byte aligned for the TMA bulk copies
   const uint64_t n_cpad = (n_ind + 15) & ~15ull;  // class rows (one byte per individual) are read as 32-bit words
-  const size_t row_bytes = n_pad * 24;
   int rc_alloc = alloc_site_buffers(c, n_sites, n_ind, true);  // same shape as last time: the device buffers are kept
   if (rc_alloc) return rc_alloc;
   c->n_sites = n_sites;
@@ -1131,10 +1167,14 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
   c->n_pad = n_pad;
   c->n_cpad = n_cpad;
   CUDA_TRY(c, cudaMemsetAsync(c->d_seg, 0, n_sites * sizeof(uint32_t), c->s_main));
-  if (n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * row_bytes, c->s_main));
-  CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, row_bytes, gl, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
-  CUDA_TRY(c, cudaMemcpyAsync(c->d_maf, maf, n_sites * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
-  c->h_maf.assign(maf, maf + n_sites);
+  if (n_pad != n_ind) CUDA_TRY(c, cudaMemsetAsync(c->d_gl, 0, n_sites * n_pad * 24, c->s_main));
+  return NGSLD_OK;
+}
+
+// Common tail: with gl, maf (and expg unless host_expg is used for the cross-check path) on the device, derive the site
+// palettes, decide about the class-compressed EM, and compute the per-site x87 terms of r2_ExpG.
+int finish_sites(ngsld_ctx *c, const double *host_expg) {
+  const uint64_t n_sites = c->n_sites, n_ind = c->n_ind, n_pad = c->n_pad, n_cpad = c->n_cpad;
   // site palettes for the class-compressed EM, and a sample of pairs to see whether it pays on this data
   c->cell_ok = c->cell_possible = false;
   c->cell_mean = c->cell_uncoded_frac = 0;
@@ -1176,13 +1216,13 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
   }
   // per-site x87 terms of the expected-genotype correlation
   const char *host_terms = getenv("NGSLD_HOST_TERMS");
-  if (host_terms && atoi(host_terms)) {
+  if (host_expg && host_terms && atoi(host_terms)) {
     // cross-check path: the host FPU's native long double instead of the device's emulation (same bits)
     std::vector<uint64_t> sig(n_sites * n_pad);
     std::vector<uint16_t> se(n_sites * n_pad);
     std::vector<double> q(n_sites);
     const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
-    hostprep::pearson_site_terms(expg, n_sites, n_ind, n_pad, nt, sig.data(), se.data(), q.data());
+    hostprep::pearson_site_terms(host_expg, n_sites, n_ind, n_pad, nt, sig.data(), se.data(), q.data());
     {  // the device table is individual-major
       std::vector<uint64_t> sig_t(sig.size());
       std::vector<uint16_t> se_t(se.size());
@@ -1200,7 +1240,6 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
     aux::site_terms_kernel<<<8, 128, 0, c->s_main>>>(nullptr, 0, 0, (uint32_t)n_pad, nullptr, nullptr, nullptr, c->d_ratio);
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   } else {
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_expg, expg, n_sites * n_ind * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
     const unsigned blocks = (unsigned)std::min<uint64_t>((n_sites + 127) / 128, (uint64_t)c->sm_count * 16);
     aux::site_terms_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_expg, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad,
                                                           c->d_dx_sig, c->d_dx_se, c->d_q, c->d_ratio);
@@ -1210,6 +1249,55 @@ int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const do
   c->h_seg.assign(n_sites, 0);
   c->h_cum.assign(n_sites, 0.0);
   return NGSLD_OK;
+}
+}  // namespace
+
+int ngsld_set_sites(ngsld_ctx *c, const double *gl, const double *expg, const double *maf, uint64_t n_sites,
+                    uint64_t n_ind) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!gl || !expg || !maf || n_sites == 0 || n_ind == 0) return fail(c, NGSLD_E_INVALID, "null or empty site arrays");
+  for (uint64_t s = 0; s < n_sites; s++)
+    if (maf[s] < 0 || maf[s] > 1) return fail(c, NGSLD_E_DATA, "invalid allele frequencies");  // gen_func.cpp:1030
+  int rc = begin_sites(c, n_sites, n_ind);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, c->n_pad * 24, gl, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_maf, maf, n_sites * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_expg, expg, n_sites * n_ind * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+  c->h_maf.assign(maf, maf + n_sites);
+  return finish_sites(c, expg);
+}
+
+int ngsld_set_sites_raw(ngsld_ctx *c, const double *raw, uint64_t n_sites, uint64_t n_ind, int log_scale, int from_log_cells,
+                        int ignore_miss_data, int call_geno, double N_thresh, double call_thresh, double *maf_out) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!raw || n_sites == 0 || n_ind == 0) return fail(c, NGSLD_E_INVALID, "null or empty site arrays");
+  if (call_geno && N_thresh > call_thresh)  // gen_func.cpp:887-888
+    return fail(c, NGSLD_E_INVALID, "missing data threshold must be smaller than calling genotype threshold!");
+  int rc = begin_sites(c, n_sites, n_ind);
+  if (rc) return rc;
+  // the file's cells go straight into the likelihood table and are prepared there, in place
+  CUDA_TRY(c, cudaMemcpy2DAsync(c->d_gl, c->n_pad * 24, raw, n_ind * 24, n_ind * 24, n_sites, cudaMemcpyHostToDevice, c->s_main));
+  int *d_flag = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d_flag, sizeof(int)));
+  CUDA_TRY(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->s_main));
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n_sites + 3) / 4, (uint64_t)c->sm_count * 16);
+  aux::prep_sites_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_gl, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)c->n_pad,
+                                                        (!from_log_cells && !log_scale) ? 1 : 0, ignore_miss_data, call_geno, N_thresh,
+                                                        call_thresh, c->d_expg, c->d_maf, d_flag);
+  int flag = 0;
+  c->h_maf.assign(n_sites, 0.0);
+  cudaError_t e1 = cudaGetLastError();
+  cudaError_t e2 = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_main);
+  cudaError_t e3 = cudaMemcpyAsync(c->h_maf.data(), c->d_maf, n_sites * sizeof(double), cudaMemcpyDeviceToHost, c->s_main);
+  cudaError_t e4 = cudaStreamSynchronize(c->s_main);
+  cudaFree(d_flag);
+  for (cudaError_t e : {e1, e2, e3, e4})
+    if (e != cudaSuccess) return fail(c, NGSLD_E_CUDA, cudaGetErrorString(e));
+  if (flag) return fail(c, NGSLD_E_DATA, "NaN found! Is the file format correct?");  // read_data.cpp:42-45
+  for (uint64_t s = 0; s < n_sites; s++)
+    if (c->h_maf[s] < 0 || c->h_maf[s] > 1) return fail(c, NGSLD_E_DATA, "invalid allele frequencies");
+  if (maf_out) memcpy(maf_out, c->h_maf.data(), n_sites * sizeof(double));
+  return finish_sites(c, nullptr);
 }
 
 int ngsld_set_positions(ngsld_ctx *c, const double *pos_dist, const char *const *labels) {
@@ -1605,6 +1693,55 @@ int ngsld_scan_decay(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_s
   CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   c->stats.d2h_bytes += n_bins * sizeof(ngsld_decay_bin) + 8;
   if (n_outside) *n_outside = outside;
+  return NGSLD_OK;
+}
+
+int ngsld_scan_edges(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, const ngsld_prune_params *q,
+                     ngsld_edge_sink sink, void *user, uint8_t *seen) {
+  if (!c) return NGSLD_E_INVALID;
+  if (!q) return fail(c, NGSLD_E_INVALID, "pruning parameters missing");
+  if (q->field < 4 || q->field > 7) return fail(c, NGSLD_E_INVALID, "weight field must be 4 (r2_ExpG), 5 (D), 6 (Dp) or 7 (r2)");
+  if (q->weight_type != 'a' && q->weight_type != 'e' && q->weight_type != 'n') return fail(c, NGSLD_E_INVALID, "weight type must be 'a', 'e' or 'n'");
+  if (q->weight_precision < 0 || q->weight_precision > 8) return fail(c, NGSLD_E_INVALID, "weight precision must be in [0,8]");
+  if (!c->d_gl) return fail(c, NGSLD_E_INVALID, "ngsld_set_sites must be called before a scan");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  dfree(c->d_seen);
+  CUDA_TRY(c, cudaMalloc(&c->d_seen, c->n_sites));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_seen, 0, c->n_sites, c->s_main));
+  c->prune_active = true;
+  c->prune_q = *q;
+  c->edge_sink = sink;
+  c->edge_user = user;
+  Delivery d;
+  d.mode = MODE_DEVICE;
+  d.rows = nullptr;
+  d.text = nullptr;
+  d.user = nullptr;
+  const int rc = run_scan(c, s1_lo, s1_hi, p, d);
+  c->prune_active = false;
+  c->edge_sink = nullptr;
+  if (rc) return rc;
+  if (seen) {
+    std::vector<unsigned char> h(c->n_sites);
+    CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_seen, c->n_sites, cudaMemcpyDeviceToHost, c->s_main));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
+    for (uint64_t s = 0; s < c->n_sites; s++)
+      if (h[s]) seen[s] = 1;
+    c->stats.d2h_bytes += c->n_sites;
+  }
+  return NGSLD_OK;
+}
+
+int ngsld_prune_graph(uint64_t n_sites, const char *const *labels, const uint8_t *seen, const ngsld_edge *edges, uint64_t n_edges,
+                      int keep_heavy, uint8_t *kept, uint32_t *excluded, uint64_t *n_excluded) {
+  if (!seen || !kept || (!edges && n_edges) || n_sites == 0) return NGSLD_E_INVALID;
+  for (uint64_t e = 0; e < n_edges; e++)
+    if (edges[e].s1 >= n_sites || edges[e].s2 >= n_sites || edges[e].s1 == edges[e].s2) return NGSLD_E_INVALID;
+  std::vector<uint32_t> rank, excl;
+  prune::label_ranks(n_sites, labels, rank);
+  prune::run(n_sites, seen, rank.data(), edges, n_edges, keep_heavy != 0, kept, excl);
+  if (excluded) memcpy(excluded, excl.data(), excl.size() * sizeof(uint32_t));
+  if (n_excluded) *n_excluded = excl.size();
   return NGSLD_OK;
 }
 

@@ -174,3 +174,28 @@ def test_fatal_errors_match_the_reference_binary(args, tmp_path):
         return lines[0] if lines else None
     assert mine.returncode == ref.returncode
     assert err_line(mine.stderr) == err_line(ref.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra,kw", [([], {}), (["--gpu_prune_keep_heavy"], dict(keep_heavy=True))])
+def test_cli_prune_mode_gives_the_pruning_scripts_site_list(extra, kw, tmp_path):
+    """--gpu_prune: the site list scripts/prune_graph.pl would produce from the TSV (restated in oracle/prune_oracle.py),
+    without the TSV ever being written; all visible GPUs."""
+    from oracle import prune_oracle as PO
+    fx = H.MANIFEST["fixtures"]["s"]
+    geno, pos = H.fixture_paths("s", tmp_path)
+    out, excl = tmp_path / "kept.txt", tmp_path / "excl.txt"
+    base = ["--geno", geno, "--probs", "--n_ind", str(fx["n_ind"]), "--n_sites", str(fx["n_sites"]), "--pos", pos,
+            "--max_kb_dist", "20", "--gpu_strict", "--verbose", "0"]
+    r = run_cli(base + ["--gpu_prune", str(out), "--gpu_prune_max_kb_dist", "10", "--gpu_prune_min_weight", "0.2",
+                        "--gpu_prune_excl", str(excl), "--gpu_stats"] + extra)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == b"" and b"[prune]" in r.stderr
+    tsv = H.oracle_tsv("s", tmp_path, fx["variants"]["kb20"]["flags"])
+    nodes, edges = PO.read_edges(tsv, max_kb_dist=10, min_weight=0.2)
+    want_kept, want_excl = PO.prune(nodes, edges, **kw)
+    got_kept = out.read_text().split()
+    assert set(got_kept) == want_kept and len(got_kept) == len(want_kept)
+    assert sorted(excl.read_text().split()) == sorted(want_excl) and len(want_excl) > 10
+    if not kw:
+        assert excl.read_text().split() == want_excl

@@ -224,3 +224,38 @@ def test_uncompressible_data_keeps_the_dense_kernel():
     import gpu_helpers
     gpu_helpers.assert_fast_close(b, strict2)
     gpu_helpers.assert_fast_close(a, strict)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(ignore_miss_data=True), dict(call_geno=True, N_thresh=0.3, call_thresh=0.9),
+                                dict(log_scale=True)])
+def test_device_side_preparation_is_close_to_the_host_path(G, kw):
+    """ngsld_set_sites_raw (K0, opt-in): likelihoods / expected genotypes / allele frequencies prepared by a kernel agree
+    with the glibc host path to a few ulp, and a scan on them stays inside the 1e-9 contract (it is NOT bit-identical:
+    CUDA's log/exp are not glibc's -- that is why the host path is the default)."""
+    GL, _ = H.gen_synth.synth(200, 330, 77)
+    GL[::9, ::4] = [1 / 3, 1 / 3, 1 / 3]
+    GL[5, 7] = [0.0, 0.0, 0.0]                     # all-zero triple: becomes flat
+    raw = np.log(GL) if kw.get("log_scale") else GL
+    if kw.get("log_scale"):
+        raw[5, 7] = [-3.0, -3.0, -3.0]
+    gl, expg, maf = N.prepare_sites(raw, **kw)
+    P = N.ScanParams.make(max_kb_dist=0, ignore_miss_data=int(kw.get("ignore_miss_data", False)))
+    with N.Engine(0) as host, N.Engine(0) as dev:
+        host.set_sites(gl, expg, maf)
+        maf_d = dev.set_sites_raw(raw, **kw)
+        a, b = host.scan(P), dev.scan(P)
+    ok = np.isfinite(maf)
+    assert np.array_equal(np.isnan(maf), np.isnan(maf_d))
+    assert np.max(np.abs(maf_d[ok] - maf[ok]) / np.maximum(maf[ok], 1e-300)) < 1e-13
+    assert np.array_equal(a["s1"], b["s1"]) and np.array_equal(a["n_used"], b["n_used"])
+    assert np.mean(a["n_iter"] != b["n_iter"]) < 1e-3          # a last-bit input change may move a pair across the 1e-5 test
+    same = a["n_iter"] == b["n_iter"]
+    for f in ("D", "hap", "r2_expg"):
+        x, y = a[f][same], b[f][same]
+        fin = np.isfinite(x) & np.isfinite(y)
+        assert np.all(np.isnan(x) == np.isnan(y)) and np.max(np.abs(x[fin] - y[fin])) < 1e-9, f
+    with pytest.raises(N.NgsldError):
+        bad = raw.copy()
+        bad[3, 3, 1] = np.nan
+        with N.Engine(0) as e:
+            e.set_sites_raw(bad, **kw)
