@@ -13,6 +13,8 @@
 //   --gpu_n INT       GPUs to use (default: all visible)
 //   --gpu_strict      bit-faithful EM kernel (hap/D/D'/r2 bit-identical to the reference; slower)
 //   --gpu_stats       print pairs, EM passes and device times per GPU to stderr
+//   --gpu_out_bin     --out receives the rows as binary records instead of TSV text: back-to-back 112-byte little-endian
+//                     ngsld_pair_row structs (include/ngsld_b200.h; numpy: ngsld_b200.ROW_DTYPE), no header, same row order
 //   --gpu_prune FILE  LD pruning fused behind the scan (what scripts/prune_graph.pl does with the TSV): no TSV is written;
 //                     FILE receives the labels of the unlinked sites that remain, one per line, in site order.  Edge filter
 //                     and options as in the script: --gpu_prune_max_kb_dist KB [inf], --gpu_prune_min_weight W [0],
@@ -84,7 +86,7 @@ struct Options {
   const char *out = nullptr;
   int n_threads = 1, verbose = 1;
   int gpu_n = 0;
-  bool gpu_strict = false, gpu_stats = false, gpu_prep = false;
+  bool gpu_strict = false, gpu_stats = false, gpu_prep = false, out_bin = false;
   const char *prune_out = nullptr, *prune_excl = nullptr;
   double prune_max_kb = INFINITY, prune_min_weight = 0;
   int prune_field = 7, prune_type = 'a';
@@ -118,6 +120,7 @@ static void parse(Options &o, int argc, char **argv) {
                                   {"gpu_strict", no_argument, NULL, 1002},
                                   {"gpu_stats", no_argument, NULL, 1003},
                                   {"gpu_prep", no_argument, NULL, 1004},
+                                  {"gpu_out_bin", no_argument, NULL, 1005},
                                   {"gpu_prune", required_argument, NULL, 1010},
                                   {"gpu_prune_max_kb_dist", required_argument, NULL, 1011},
                                   {"gpu_prune_min_weight", required_argument, NULL, 1012},
@@ -152,6 +155,7 @@ static void parse(Options &o, int argc, char **argv) {
       case 1002: o.gpu_strict = true; break;
       case 1003: o.gpu_stats = true; break;
       case 1004: o.gpu_prep = true; break;
+      case 1005: o.out_bin = true; break;
       case 1010: o.prune_out = optarg; break;
       case 1011: o.prune_max_kb = atof(optarg); break;
       case 1012: o.prune_min_weight = atof(optarg); break;
@@ -226,8 +230,9 @@ int main(int argc, char **argv) {
     return true;
   };
   char header[512];
-  const int hl = ngsld_tsv_header(o.extend_out, header, sizeof header);
-  if (!prune_mode && !write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
+  const int hl_text = ngsld_tsv_header(o.extend_out, header, sizeof header);
+  const int hl = o.out_bin ? 0 : hl_text;
+  if (!prune_mode && hl && !write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
 
   const double t_start = wall_s();
   if (o.verbose >= 1) fprintf(stderr, "> Reading data from file...\n");
@@ -435,7 +440,7 @@ int main(int argc, char **argv) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to plan the pair scan!");
   }
-  const uint64_t row_bound = ngsld_tsv_row_bound(ctx[0], o.extend_out);
+  const uint64_t row_bound = o.out_bin ? sizeof(ngsld_pair_row) : ngsld_tsv_row_bound(ctx[0], o.extend_out);
   uint64_t buf_bytes = 512ull << 20;  // per slab buffer; a scan drains its chunk pipeline at the end, so slabs stay long
   if (const char *e = getenv("NGSLD_CLI_BUF_MB"))
     if (atoll(e) > 0) buf_bytes = (uint64_t)atoll(e) << 20;
@@ -571,7 +576,13 @@ int main(int argc, char **argv) {
           acc[g].s_wait += ts0 - tw0;
           uint64_t nb = 0, nr = 0;
           std::string spill;
-          int rc = ngsld_scan_tsv_into(ctx[g], bounds[k], bounds[k + 1], &P, bufs[bi].p, cap, &nb, &nr);
+          int rc;
+          if (o.out_bin) {
+            rc = ngsld_scan_into(ctx[g], bounds[k], bounds[k + 1], &P, (ngsld_pair_row *)bufs[bi].p, cap / sizeof(ngsld_pair_row), &nr);
+            nb = nr * sizeof(ngsld_pair_row);
+          } else {
+            rc = ngsld_scan_tsv_into(ctx[g], bounds[k], bounds[k + 1], &P, bufs[bi].p, cap, &nb, &nr);
+          }
           ngsld_scan_stats st;
           ngsld_get_stats(ctx[g], &st);
           if (rc == NGSLD_E_INVALID && strstr(ngsld_last_error(ctx[g]), "too small")) {

@@ -680,9 +680,11 @@ void build_tiles(const Plan &pl, uint32_t ca, uint32_t cb, uint32_t TA, uint32_t
   block_off.push_back(tiles.size());
 }
 
+// rows_dst (MODE_ROWS only, may be NULL): the chunk's rows are copied from the device straight to rows_dst + r0 (the
+// caller's buffer for the whole scan) instead of the context's page-locked staging chunk.
 int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const EmChoice &ch, ChunkBuf &b,
                  unsigned long long r0, unsigned long long r1, size_t t0, size_t t1, ScanMode mode,
-                 const fmt::FormatArgs *fa) {
+                 const fmt::FormatArgs *fa, ngsld_pair_row *rows_dst = nullptr) {
   const unsigned long long n = r1 - r0;
   const SiteTable T = site_table(c);
   PairChunk C;
@@ -807,7 +809,8 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   } else if (mode == MODE_ROWS) {
     CUDA_TRY(c, cudaEventRecord(b.ev_f0, c->s_main));  // join point
     CUDA_TRY(c, cudaStreamWaitEvent(c->s_copy, b.ev_f0, 0));
-    CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, n * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
+    CUDA_TRY(c, cudaMemcpyAsync(rows_dst ? rows_dst + r0 : b.h_rows, b.d_rows, n * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost,
+                                c->s_copy));
     CUDA_TRY(c, cudaEventRecord(b.ev_done, c->s_copy));
     c->stats.d2h_bytes += n * sizeof(ngsld_pair_row);
   }
@@ -828,6 +831,8 @@ struct Delivery {
   char *text_dst = nullptr;
   uint64_t text_cap = 0;
   uint64_t *text_len = nullptr;
+  // MODE_ROWS without a sink: rows go straight from the device into one caller buffer (ngsld_scan_into)
+  ngsld_pair_row *rows_dst = nullptr;
 };
 
 int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
@@ -919,6 +924,7 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   if (rc) return rc;
   c->stats.ms_plan = now_ms() - t_plan0;
   if (pl.total == 0) return NGSLD_OK;
+  if (d.rows_dst && pl.total > d.text_cap) return fail(c, NGSLD_E_INVALID, "output buffer too small for this scan");
   EmChoice ch;
   rc = choose_em(c, pl, ch);
   if (rc) return rc;
@@ -987,7 +993,7 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
     } else {
       r1 = std::min<unsigned long long>(pl.total, r0 + chunk);
     }
-    rc = launch_chunk(c, pl, P, ch, b, r0, r1, t0, t1, d.mode, &fa);
+    rc = launch_chunk(c, pl, P, ch, b, r0, r1, t0, t1, d.mode, &fa, d.rows_dst);
     if (rc) return rc;
     r0 = r1;
     k++;
@@ -1499,33 +1505,20 @@ int ngsld_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_pa
   return run_scan(c, s1_lo, s1_hi, p, d);
 }
 
-namespace {
-struct IntoState {
-  ngsld_pair_row *out;
-  uint64_t cap, n;
-};
-int into_sink(void *u, const ngsld_pair_row *rows, uint64_t n) {
-  IntoState *st = (IntoState *)u;
-  if (st->n + n > st->cap) return 1;
-  memcpy(st->out + st->n, rows, n * sizeof(ngsld_pair_row));
-  st->n += n;
-  return 0;
-}
-}  // namespace
-
 int ngsld_scan_into(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_params *p, ngsld_pair_row *out,
                     uint64_t cap, uint64_t *n_rows) {
   if (!c) return NGSLD_E_INVALID;
   if (!out && cap) return fail(c, NGSLD_E_INVALID, "output buffer missing");
-  IntoState st = {out, cap, 0};
+  ngsld_pair_row dummy;
   Delivery d;
   d.mode = MODE_ROWS;
-  d.rows = into_sink;
+  d.rows = nullptr;
   d.text = nullptr;
-  d.user = &st;
+  d.user = nullptr;
+  d.rows_dst = out ? out : &dummy;  // every chunk is copied from the device to out + its row offset, no staging
+  d.text_cap = cap;                 // (capacity in rows)
   int rc = run_scan(c, s1_lo, s1_hi, p, d);
-  if (rc == NGSLD_E_SINK) return fail(c, NGSLD_E_INVALID, "output buffer too small for this scan");
-  if (n_rows) *n_rows = st.n;
+  if (n_rows) *n_rows = rc ? 0 : c->stats.n_pairs;
   return rc;
 }
 

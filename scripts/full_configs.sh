@@ -15,6 +15,15 @@ case $CFG in
   cfg5) NS=${NS5:-1000000}; NI=2000; SEED=13; FLAGS="--max_kb_dist 0 --rnd_sample 0.01 --seed 1"; CHECK="--head 60000 --rnd-sample 0.01 --seed 1 --s1-hi 8000" ;;
   *) echo "unknown config $CFG"; exit 2 ;;
 esac
+# host memory: the input file (tmpfs) + the CLI's in-place genotype matrix + expected genotypes (8 B per cell) + buffers;
+# a box that cannot hold the stated size gets the largest prefix that fits (and says so) instead of an OOM kill
+AVAIL_GB=$(awk '/MemAvailable/{print int($2/1048576)}' /proc/meminfo)
+NEED_GB=$(( NS * NI * 56 / 1000000000 + 40 ))
+if [ $NEED_GB -gt $AVAIL_GB ]; then
+  NS_FIT=$(( (AVAIL_GB - 40) * 1000000000 / (NI * 56) / 1000 * 1000 ))
+  echo "[$CFG] only $AVAIL_GB GB of host memory available, $NEED_GB GB needed for $NS sites: scaling down to $NS_FIT sites"
+  NS=$NS_FIT
+fi
 G=$D/$CFG.glf
 s=$(date +%s%N)
 [ -f $G ] || python scripts/gen_big.py $NS $NI $SEED $G

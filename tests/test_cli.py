@@ -199,3 +199,26 @@ def test_cli_prune_mode_gives_the_pruning_scripts_site_list(extra, kw, tmp_path)
     assert sorted(excl.read_text().split()) == sorted(want_excl) and len(want_excl) > 10
     if not kw:
         assert excl.read_text().split() == want_excl
+
+
+@pytest.mark.gpu
+def test_cli_binary_side_format(tmp_path):
+    """--gpu_out_bin: --out holds the rows as 112-byte records in the TSV's row order; formatting them gives the TSV."""
+    import numpy as np
+    import ngsld_b200 as N
+    v = H.MANIFEST["fixtures"]["tiny"]["variants"]["ext"]
+    args = ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--pos", TINY + ".pos"] + v["flags"]
+    out = tmp_path / "o.bin"
+    r = run_cli(args + ["--gpu_strict", "--gpu_out_bin", "--verbose", "0", "--out", str(out)],
+                env=dict(os.environ, NGSLD_CLI_SLAB_ROWS="100"))
+    assert r.returncode == 0, r.stderr.decode()
+    rows = np.fromfile(out, N.ROW_DTYPE)
+    gold = H.golden_bytes("tiny", "ext").decode().splitlines()[1:]
+    assert len(rows) == len(gold) == v["rows"]
+    labels = [l.replace("\t", ":") for l in open(TINY + ".pos").read().splitlines()]
+    for row, line in list(zip(rows, gold))[::7]:
+        f = line.split("\t")
+        assert (labels[row["s1"]], labels[row["s2"]]) == (f[0], f[1])
+        assert "%.0f" % row["dist"] == f[2] and int(f[-1]) == row["n_iter"] and int(f[7]) == row["n_used"]
+        for val, txt in zip([row["r2_expg"], row["D"], row["Dp"], row["r2"]], f[3:7]):
+            assert ("%f" % val).replace("nan", "-nan").replace("--", "-") == txt
