@@ -298,24 +298,31 @@ def strong_legs(a, eng, P, N, GL, pos, bounds, rank, world, local, barrier, redu
         target = a.strong_out
         if not target:
             target = flag + ".ld" if shutil.disk_usage("/dev/shm").free > 130e9 else "/dev/null"
-        cmd = [cli, "--geno", geno, "--probs", "--n_ind", str(a.n_ind), "--n_sites", str(a.n_sites), "--pos", geno + ".pos",
-               "--max_kb_dist", "0", "--gpu_n", str(world), "--gpu_stats", "--verbose", "0", "--out", target]
-        t1 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        dt = time.perf_counter() - t1
-        size = os.path.getsize(target) if target != "/dev/null" and os.path.exists(target) else None
-        rows = None
-        tl = [l for l in r.stderr.splitlines() if l.startswith("[time]")]
-        wl = [l for l in r.stderr.splitlines() if l.startswith("[writer")]
-        if target != "/dev/null" and os.path.exists(target):
-            os.unlink(target)
+        base = [cli, "--geno", geno, "--probs", "--n_ind", str(a.n_ind), "--n_sites", str(a.n_sites), "--pos", geno + ".pos",
+                "--max_kb_dist", "0", "--gpu_n", str(world), "--gpu_stats", "--verbose", "0", "--out", target]
+
+        def cli_leg(extra, what):
+            import glob
+            t1 = time.perf_counter()
+            r = subprocess.run(base + extra, capture_output=True, text=True)
+            dt = time.perf_counter() - t1
+            files = [target] if target != "/dev/null" and os.path.exists(target) else []
+            if extra and target != "/dev/null":
+                files = sorted(glob.glob(target + ".part-*"))
+            size = sum(os.path.getsize(f) for f in files) if files else None
+            for f in files:
+                os.unlink(f)
+            err = r.stderr.splitlines()
+            return {"seconds": dt, "returncode": r.returncode, "pairs_per_s": n_total / dt if r.returncode == 0 else None,
+                    "out": target if target == "/dev/null" else "/dev/shm (tmpfs), " + what, "tsv_bytes": size, "files": len(files),
+                    "time_line": next((l for l in err if l.startswith("[time]")), None),
+                    "writers": [l for l in err if l.startswith("[writer")],
+                    "command": "ngsLD --geno <600 MB binary GL> --probs --n_ind 500 --n_sites 50000 --pos <pos> --max_kb_dist 0 "
+                               f"--gpu_n {world} --out <out> {' '.join(extra)}: process start to exit"}
+        out["tsv_cli"] = cli_leg([], "one file (the reference's --out)")
+        out["tsv_cli_shards"] = cli_leg(["--gpu_out_shards"], "one file per slab of first sites, cat in name order = the output")
         for f in (geno, geno + ".pos"):
             os.unlink(f)
-        out["tsv_cli"] = {"seconds": dt, "returncode": r.returncode, "pairs_per_s": n_total / dt if r.returncode == 0 else None,
-                          "out": target if target == "/dev/null" else "/dev/shm (tmpfs)", "tsv_bytes": size,
-                          "time_line": tl[0] if tl else None, "writers": wl,
-                          "command": "ngsLD --geno <600 MB binary GL> --probs --n_ind 500 --n_sites 50000 --pos <pos> "
-                                     f"--max_kb_dist 0 --gpu_n {world} --out <out>: process start to exit"}
         open(flag + ".done", "w").close()
     elif os.path.exists(cli):
         while not os.path.exists(flag + ".done"):  # wait on the CPU: a pending NCCL barrier would occupy SMs

@@ -15,6 +15,9 @@
 //   --gpu_stats       print pairs, EM passes and device times per GPU to stderr
 //   --gpu_out_bin     --out receives the rows as binary records instead of TSV text: back-to-back 112-byte little-endian
 //                     ngsld_pair_row structs (include/ngsld_b200.h; numpy: ngsld_b200.ROW_DTYPE), no header, same row order
+//   --gpu_out_shards  write one file per slab of first sites, <out>.part-000000, <out>.part-000001, ... (the header is in the
+//                     first): `cat <out>.part-*` is the output.  Writes to ONE file are serialised by the kernel (one inode
+//                     lock: ~3.4 GB/s into the page cache however many threads write); separate files are written in parallel
 //   --gpu_prune FILE  LD pruning fused behind the scan (what scripts/prune_graph.pl does with the TSV): no TSV is written;
 //                     FILE receives the labels of the unlinked sites that remain, one per line, in site order.  Edge filter
 //                     and options as in the script: --gpu_prune_max_kb_dist KB [inf], --gpu_prune_min_weight W [0],
@@ -36,6 +39,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -86,7 +90,7 @@ struct Options {
   const char *out = nullptr;
   int n_threads = 1, verbose = 1;
   int gpu_n = 0;
-  bool gpu_strict = false, gpu_stats = false, gpu_prep = false, out_bin = false;
+  bool gpu_strict = false, gpu_stats = false, gpu_prep = false, out_bin = false, out_shards = false;
   const char *prune_out = nullptr, *prune_excl = nullptr;
   double prune_max_kb = INFINITY, prune_min_weight = 0;
   int prune_field = 7, prune_type = 'a';
@@ -121,6 +125,7 @@ static void parse(Options &o, int argc, char **argv) {
                                   {"gpu_stats", no_argument, NULL, 1003},
                                   {"gpu_prep", no_argument, NULL, 1004},
                                   {"gpu_out_bin", no_argument, NULL, 1005},
+                                  {"gpu_out_shards", no_argument, NULL, 1006},
                                   {"gpu_prune", required_argument, NULL, 1010},
                                   {"gpu_prune_max_kb_dist", required_argument, NULL, 1011},
                                   {"gpu_prune_min_weight", required_argument, NULL, 1012},
@@ -156,6 +161,7 @@ static void parse(Options &o, int argc, char **argv) {
       case 1003: o.gpu_stats = true; break;
       case 1004: o.gpu_prep = true; break;
       case 1005: o.out_bin = true; break;
+      case 1006: o.out_shards = true; break;
       case 1010: o.prune_out = optarg; break;
       case 1011: o.prune_max_kb = atof(optarg); break;
       case 1012: o.prune_min_weight = atof(optarg); break;
@@ -211,14 +217,15 @@ int main(int argc, char **argv) {
   // written with pwrite() by several writer threads at offsets that are known as soon as all earlier slabs have been
   // formatted; a pipe / terminal / device gets the slabs in order from one writer.
   const bool prune_mode = o.prune_out != nullptr;
+  const bool shards = o.out_shards && o.out && !prune_mode;
   int out_fd = STDOUT_FILENO;
-  if (o.out && !prune_mode) out_fd = open(o.out, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (o.out && !prune_mode && !shards) out_fd = open(o.out, O_WRONLY | O_CREAT | O_TRUNC, 0666);
   if (out_fd < 0) die(fn, "cannot open output file!");
   struct stat ost;
   const bool seekable = fstat(out_fd, &ost) == 0 && S_ISREG(ost.st_mode);
-  auto write_all = [&](const char *p, size_t n, off_t off) -> bool {  // off < 0: sequential write()
+  auto write_all = [&](int fd, const char *p, size_t n, off_t off) -> bool {  // off < 0: sequential write()
     while (n) {
-      const ssize_t w = off >= 0 ? pwrite(out_fd, p, n, off) : write(out_fd, p, n);
+      const ssize_t w = off >= 0 ? pwrite(fd, p, n, off) : write(fd, p, n);
       if (w < 0) {
         if (errno == EINTR) continue;
         return false;
@@ -232,7 +239,7 @@ int main(int argc, char **argv) {
   char header[512];
   const int hl_text = ngsld_tsv_header(o.extend_out, header, sizeof header);
   const int hl = o.out_bin ? 0 : hl_text;
-  if (!prune_mode && hl && !write_all(header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
+  if (!prune_mode && !shards && hl && !write_all(out_fd, header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
 
   const double t_start = wall_s();
   if (o.verbose >= 1) fprintf(stderr, "> Reading data from file...\n");
@@ -459,7 +466,7 @@ int main(int argc, char **argv) {
 
   if (o.verbose >= 1) fprintf(stderr, "==> Waiting for all threads to finish...\n");
   // one pwrite() stream into the page cache moves ~3.5 GB/s; a GPU produces ~4 GB/s of text
-  const int n_writers = seekable ? std::max(2, std::min(2 * n_gpu, 16)) : 1;
+  const int n_writers = shards ? std::max(2, std::min(2 * n_gpu, 16)) : seekable ? 2 : 1;
   const int n_bufs = n_gpu + n_writers + 1;
   struct Buf {
     char *p = nullptr;
@@ -488,7 +495,7 @@ int main(int argc, char **argv) {
     int buf = -1;
     uint64_t bytes = 0, rows = 0;
     off_t offset = -1;          // known once every earlier slab has been formatted
-    bool done = false, taken = false;
+    bool done = false;
     std::string spill;          // only when a slab outgrew its buffer (values the host formatter had to print)
   };
   std::vector<Slab> slab(n_slabs);
@@ -496,8 +503,9 @@ int main(int argc, char **argv) {
   std::condition_variable cv;
   std::vector<int> free_bufs;
   for (int k = 0; k < n_bufs; k++) free_bufs.push_back(k);
-  int next_slab = 0, next_off = 0, next_seq = 0, written = 0;
-  off_t cursor = hl;
+  int next_slab = 0, next_off = 0, written = 0;
+  std::deque<int> ready;  // slabs that can be written now: formatted and (one file) with their offset known
+  off_t cursor = shards ? 0 : hl;
   bool failed = false, write_failed = false;
   struct PerGpu {
     uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0, cells = 0, cell_pairs = 0, resid = 0;
@@ -517,25 +525,23 @@ int main(int argc, char **argv) {
         int k = -1;
         {
           std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&]() {
-            if (failed || written == n_slabs) return true;
-            if (!seekable) return next_seq < next_off && !slab[next_seq].taken;
-            for (int j = written; j < next_off; j++)
-              if (!slab[j].taken) return true;
-            return false;
-          });
+          cv.wait(lk, [&]() { return failed || written == n_slabs || !ready.empty(); });
           if (failed || written == n_slabs) return;
-          if (!seekable) {
-            k = next_seq;
-          } else {
-            for (int j = written; j < next_off && k < 0; j++)
-              if (!slab[j].taken) k = j;
-          }
-          slab[k].taken = true;
+          k = ready.front();
+          ready.pop_front();
         }
         const double t0 = wall_s();
         const char *src = slab[k].spill.empty() ? bufs[slab[k].buf].p : slab[k].spill.data();
-        const bool ok = write_all(src, slab[k].bytes, seekable ? slab[k].offset : -1);
+        bool ok;
+        if (shards) {  // a file of its own: no offset to wait for, no lock shared with the other writers
+          char path[4096];
+          snprintf(path, sizeof path, "%s.part-%06d", o.out, k);
+          const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+          ok = fd >= 0 && (k != 0 || hl == 0 || write_all(fd, header, (size_t)hl, -1)) && write_all(fd, src, slab[k].bytes, -1);
+          if (fd >= 0 && close(fd) != 0) ok = false;
+        } else {
+          ok = write_all(out_fd, src, slab[k].bytes, seekable ? slab[k].offset : -1);
+        }
         wacc[w].s_write += wall_s() - t0;
         wacc[w].bytes += slab[k].bytes;
         {
@@ -543,8 +549,7 @@ int main(int argc, char **argv) {
           if (!ok) failed = write_failed = true;
           free_bufs.push_back(slab[k].buf);
           std::string().swap(slab[k].spill);
-          if (!seekable) next_seq++;
-          written++;  // writers take the lowest slab not yet taken, so every slab below index `written` is taken
+          written++;
         }
         cv.notify_all();
       }
@@ -608,9 +613,14 @@ int main(int argc, char **argv) {
               slab[k].rows = nr;
               slab[k].spill.swap(spill);
               slab[k].done = true;
-              while (next_off < n_slabs && slab[next_off].done && slab[next_off].offset < 0) {
+              if (shards) {
+                ready.push_back(k);
+                cursor += (off_t)nb;
+              }
+              while (!shards && next_off < n_slabs && slab[next_off].done) {  // offsets follow from the sizes of all earlier slabs
                 slab[next_off].offset = cursor;
                 cursor += (off_t)slab[next_off].bytes;
+                ready.push_back(next_off);
                 next_off++;
               }
             }
@@ -644,10 +654,10 @@ int main(int argc, char **argv) {
     }
     for (int w = 0; w < n_writers; w++)
       fprintf(stderr, "[writer %d] %.2f GB in %.2f s of %s = %.2f GB/s\n", w, wacc[w].bytes / 1e9, wacc[w].s_write,
-              seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
+              shards ? "write to slab files" : seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
     fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, allocated in %.2f s)\n",
             t_read - t_start, t_prep - t_read, n_gpu, t_upload - t_prep, host_upload_all || n_gpu == 1 ? "from the host" : "one upload, then GPU to GPU",
-            t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - hl) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
+            t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - (shards ? 0 : hl)) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
             bufs[0].pinned ? "page-locked" : "pageable", t_alloc);
   }
   if (o.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");

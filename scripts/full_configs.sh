@@ -31,11 +31,11 @@ e=$(date +%s%N); echo "[$CFG] input: $NS sites x $NI individuals, $(du -h $G | c
 free -g | head -2
 for n in $GPUS; do
   s=$(date +%s%N)
-  $CLI --geno $G --probs --n_ind $NI --n_sites $NS --pos $G.pos $FLAGS --gpu_n $n --gpu_stats --verbose 0 --out $OUT 2> $D/$CFG.err
+  $CLI --geno $G --probs --n_ind $NI --n_sites $NS --pos $G.pos $FLAGS --gpu_n $n --gpu_stats --verbose 0 --out $OUT ${CLI_EXTRA:-} 2> $D/$CFG.err
   rc=$?; e=$(date +%s%N)
   echo "[$CFG] $n GPU(s): rc=$rc, process start -> exit $(( (e - s) / 1000000 )) ms, out=$OUT"
   grep -E "^\[(gpu|writer|time)" $D/$CFG.err
-  [ "$OUT" != "/dev/null" ] && { ls -la $OUT; rm -f $OUT; }
+  [ "$OUT" != "/dev/null" ] && { ls -la $OUT* | head -3; du -ch $OUT* | tail -1; rm -f $OUT $OUT.part-*; }
 done
 if [ "${NO_CHECK:-0}" = "0" ]; then
   echo "[$CFG] fast vs bit-faithful kernel on a sample:"

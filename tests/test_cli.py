@@ -222,3 +222,17 @@ def test_cli_binary_side_format(tmp_path):
         assert "%.0f" % row["dist"] == f[2] and int(f[-1]) == row["n_iter"] and int(f[7]) == row["n_used"]
         for val, txt in zip([row["r2_expg"], row["D"], row["Dp"], row["r2"]], f[3:7]):
             assert ("%f" % val).replace("nan", "-nan").replace("--", "-") == txt
+
+
+@pytest.mark.gpu
+def test_cli_slab_files_concatenate_to_the_output(tmp_path):
+    """--gpu_out_shards: one file per slab, written in parallel; cat in name order is the reference's file."""
+    v = H.MANIFEST["fixtures"]["tiny"]["variants"]["ext"]
+    args = ["--geno", TINY, "--n_ind", "24", "--n_sites", "40", "--pos", TINY + ".pos"] + v["flags"]
+    out = tmp_path / "o.ld"
+    r = run_cli(args + ["--gpu_strict", "--gpu_out_shards", "--verbose", "0", "--gpu_stats", "--out", str(out)],
+                env=dict(os.environ, NGSLD_CLI_SLAB_ROWS="97"))
+    assert r.returncode == 0, r.stderr.decode()
+    parts = sorted(tmp_path.glob("o.ld.part-*"))
+    assert len(parts) >= 5 and not out.exists()
+    assert b"".join(p.read_bytes() for p in parts) == H.golden_bytes("tiny", "ext")
