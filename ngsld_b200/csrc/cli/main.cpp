@@ -473,24 +473,6 @@ int main(int argc, char **argv) {
     bool pinned = false;
   };
   std::vector<Buf> bufs(n_bufs);
-  const double t_alloc0 = wall_s();
-  {
-    std::vector<std::thread> th;  // page-locking is kernel work per page: in parallel
-    for (auto &b : bufs)
-      th.emplace_back([&b, cap]() {
-        void *q = nullptr;
-        if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
-          b.p = (char *)q;
-          b.pinned = true;
-        } else {
-          b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
-        }
-      });
-    for (auto &t : th) t.join();
-  }
-  for (auto &b : bufs)
-    if (!b.p) die(fn, "cannot allocate the output buffers!");
-  const double t_alloc = wall_s() - t_alloc0;
   struct Slab {
     int buf = -1;
     uint64_t bytes = 0, rows = 0;
@@ -502,7 +484,7 @@ int main(int argc, char **argv) {
   std::mutex mu;
   std::condition_variable cv;
   std::vector<int> free_bufs;
-  for (int k = 0; k < n_bufs; k++) free_bufs.push_back(k);
+  bool alloc_failed = false;
   int next_slab = 0, next_off = 0, written = 0;
   std::deque<int> ready;  // slabs that can be written now: formatted and (one file) with their offset known
   off_t cursor = shards ? 0 : hl;
@@ -517,6 +499,31 @@ int main(int argc, char **argv) {
     double s_write = 0;
   };
   std::vector<PerWriter> wacc(n_writers);
+
+  // The slab buffers are page-locked in the background (that is kernel work per page, ~0.2 s per buffer): the GPUs start on
+  // the first ones while the rest are still being allocated.
+  const double t_alloc0 = wall_s();
+  double t_alloc = 0;
+  std::vector<std::thread> allocators;
+  for (int k = 0; k < n_bufs; k++)
+    allocators.emplace_back([&, k]() {
+      void *q = nullptr;
+      Buf b;
+      if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
+        b.p = (char *)q;
+        b.pinned = true;
+      } else {
+        b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        bufs[k] = b;
+        if (b.p) free_bufs.push_back(k);
+        else alloc_failed = failed = true;
+        t_alloc = wall_s() - t_alloc0;
+      }
+      cv.notify_all();
+    });
 
   std::vector<std::thread> writers;
   for (int w = 0; w < n_writers; w++)
@@ -634,6 +641,8 @@ int main(int argc, char **argv) {
   const double t_scan1 = wall_s();
   cv.notify_all();
   for (auto &t : writers) t.join();
+  for (auto &t : allocators) t.join();
+  if (alloc_failed) die(fn, "cannot allocate the output buffers!");
   const double t_done = wall_s();
   for (int g = 0; g < n_gpu; g++)
     if (rcs[g]) {
@@ -655,7 +664,7 @@ int main(int argc, char **argv) {
     for (int w = 0; w < n_writers; w++)
       fprintf(stderr, "[writer %d] %.2f GB in %.2f s of %s = %.2f GB/s\n", w, wacc[w].bytes / 1e9, wacc[w].s_write,
               shards ? "write to slab files" : seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
-    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, allocated in %.2f s)\n",
+    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, all of them allocated %.2f s into the scan)\n",
             t_read - t_start, t_prep - t_read, n_gpu, t_upload - t_prep, host_upload_all || n_gpu == 1 ? "from the host" : "one upload, then GPU to GPU",
             t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - (shards ? 0 : hl)) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
             bufs[0].pinned ? "page-locked" : "pageable", t_alloc);
