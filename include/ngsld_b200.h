@@ -189,6 +189,8 @@ int ngsld_scan_tsv_into(ngsld_ctx *ctx, uint64_t s1_lo, uint64_t s1_hi, const ng
                         uint64_t *n_bytes, uint64_t *n_rows);
 /* upper bound of the bytes of one TSV row the device formatter writes (depends on the longest label). */
 uint64_t ngsld_tsv_row_bound(const ngsld_ctx *ctx, int extend_out);
+/* the same bound before any context exists, from the length of the longest site label (6 = "(null)" without labels). */
+uint64_t ngsld_tsv_row_bound_for(uint32_t max_label_len, int extend_out);
 /* page-locked host memory usable from every device (cudaHostAlloc, portable), for result buffers that the GPUs fill
  * by DMA and a writer thread hands to write(2) as they are. */
 int ngsld_alloc_host(void **p, size_t bytes);

@@ -114,6 +114,7 @@ def load_library():
         "ngsld_scan_device": (i32, [vp, u64, u64, C.POINTER(ScanParams)]),
         "ngsld_scan_tsv_into": (i32, [vp, u64, u64, C.POINTER(ScanParams), vp, u64, C.POINTER(u64), C.POINTER(u64)]),
         "ngsld_tsv_row_bound": (u64, [vp, i32]),
+        "ngsld_tsv_row_bound_for": (u64, [C.c_uint32, i32]),
         "ngsld_alloc_host": (i32, [C.POINTER(vp), C.c_size_t]),
         "ngsld_free_host": (None, [vp]),
         "ngsld_share_sites": (i32, [vp, vp]),
@@ -145,7 +146,7 @@ EXPORTED = ["ngsld_abi_version", "ngsld_device_count", "ngsld_create", "ngsld_de
             "ngsld_scan_tsv", "ngsld_scan_device", "ngsld_get_stats", "ngsld_pairs", "ngsld_site_seeds",
             "ngsld_tsv_header", "ngsld_probe_fp64", "ngsld_plan_count", "ngsld_plan_partition", "ngsld_load_geno",
             "ngsld_load_positions", "ngsld_free", "ngsld_scan_decay", "ngsld_scan_tsv_into", "ngsld_tsv_row_bound",
-            "ngsld_alloc_host", "ngsld_free_host", "ngsld_share_sites", "ngsld_set_sites_raw", "ngsld_scan_edges", "ngsld_prune_graph"]
+            "ngsld_alloc_host", "ngsld_free_host", "ngsld_share_sites", "ngsld_set_sites_raw", "ngsld_scan_edges", "ngsld_prune_graph", "ngsld_tsv_row_bound_for"]
 
 
 def prepare_sites(raw, log_scale=False, from_log_cells=False, ignore_miss_data=False, call_geno=False,

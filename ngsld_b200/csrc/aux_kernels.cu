@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
 __global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad,
                                                          uint64_t *dx_sig, uint16_t *dx_se, double *q, uint64_t *ratio) {
   // the ratio table shared by every pair: significand of (long double)(i / (i + 1.0))
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_pad; i += gridDim.x * blockDim.x)  // n_pad + 1 entries
     ratio[i] = i ? x87::ratio_sig(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0))) : 0ull;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
     const double *x = expg + (size_t)s * n_ind;
@@ -196,31 +196,87 @@ struct Taus {
   }
 };
 
+// One CTA per first site; the site's candidate stream is cut into segments of TAUS_SEG draws and every thread takes one
+// segment at a time, starting in the middle of the stream: each component of the generator is linear over GF(2), so the
+// state after 512 * 2^j draws is a bit-matrix product with a precomputed table (hostprep::taus_jump_tables).  A site with
+// a million candidates (BASELINE config 5) is thus walked by the whole CTA at once instead of by a single thread.
+// A draw is kept iff !(get() / 2^32 > rnd_sample)  <=>  get() <= keep_max = floor(rnd_sample * 2^32) (both scalings by a
+// power of two are exact).
 // mode 0: counts[c1 - c_lo] = kept pairs; mode 1: write the kept partners at row_off[c1] - row_base.
-__global__ void taus_sample_kernel(const unsigned long long *site_seeds, const uint32_t *cs, const uint32_t *cw_end,
-                                   uint32_t c_lo, uint32_t c_hi, double rnd_sample, int mode,
-                                   unsigned long long *counts, const unsigned long long *row_off,
-                                   unsigned long long row_base, unsigned long long row_cap, uint32_t *s1,
-                                   uint32_t *s2) {
-  for (uint32_t c1 = c_lo + blockIdx.x * blockDim.x + threadIdx.x; c1 < c_hi; c1 += gridDim.x * blockDim.x) {
+constexpr int TAUS_SEG = 512;
+constexpr int TAUS_CTA = 256;
+
+__device__ __forceinline__ uint32_t gf2_apply(const uint32_t *cols, uint32_t x) {
+  uint32_t y = 0;
+#pragma unroll 8
+  for (int b = 0; b < 32; b++) y ^= cols[b] & (0u - ((x >> b) & 1u));
+  return y;
+}
+
+__global__ void __launch_bounds__(TAUS_CTA) taus_sample_kernel(const unsigned long long *site_seeds, const uint32_t *cs,
+                                                               const uint32_t *cw_end, uint32_t c_lo, uint32_t c_hi,
+                                                               uint32_t keep_max, int mode, unsigned long long *counts,
+                                                               const unsigned long long *row_off, unsigned long long row_base,
+                                                               unsigned long long row_cap, uint32_t *s1, uint32_t *s2,
+                                                               const uint32_t *jump) {
+  __shared__ unsigned int warp_tot[TAUS_CTA / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t c1 = c_lo + blockIdx.x; c1 < c_hi; c1 += gridDim.x) {
     const uint32_t site = cs ? cs[c1] : c1;
-    Taus g;
-    g.set(site_seeds[site]);
-    unsigned long long kept = 0;
-    const unsigned long long base = mode ? row_off[c1] - row_base : 0;
-    for (uint32_t c2 = c1 + 1; c2 < cw_end[c1]; c2++) {
-      const double u = __dmul_rn(__ddiv_rn((double)g.get(), 4294967296.0), 1.0);
-      if (u > rnd_sample) continue;
-      if (mode) {
-        const unsigned long long o = base + kept;
-        if (o < row_cap) {
-          s1[o] = site;
-          s2[o] = cs ? cs[c2] : c2;
-        }
+    const uint32_t first = c1 + 1, end = cw_end[c1];
+    const unsigned long long W = end > first ? end - first : 0u;  // candidate partners, in stream order
+    Taus g0;
+    g0.set(site_seeds[site]);
+    const unsigned long long n_seg = (W + TAUS_SEG - 1) / TAUS_SEG;
+    const unsigned long long base = mode ? row_off[c1] - row_base : 0;  // may wrap: rows before the chunk fail o < row_cap
+    unsigned long long running = 0;  // kept draws of the segments before this round (the same in every thread)
+    for (unsigned long long seg0 = 0; seg0 < n_seg; seg0 += TAUS_CTA) {
+      const unsigned long long k = seg0 + tid;
+      Taus g = g0;
+      unsigned int cnt = 0;
+      const unsigned long long lo = k * TAUS_SEG, hi = lo + TAUS_SEG < W ? lo + TAUS_SEG : W;
+      if (k < n_seg) {
+        for (int j = 0; (k >> j) != 0; j++)
+          if ((k >> j) & 1ull) {
+            g.a = gf2_apply(jump + (j * 3 + 0) * 32, g.a);
+            g.b = gf2_apply(jump + (j * 3 + 1) * 32, g.b);
+            g.c = gf2_apply(jump + (j * 3 + 2) * 32, g.c);
+          }
+        Taus w = g;
+        for (unsigned long long i = lo; i < hi; i++) cnt += w.get() <= keep_max ? 1u : 0u;
       }
-      kept++;
+      // exclusive prefix of cnt over the CTA
+      unsigned int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      unsigned int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < TAUS_CTA / 32; w++) {
+        const unsigned int t = warp_tot[w];
+        if (w < warp) before += t;
+        total += t;
+      }
+      __syncthreads();
+      if (mode && k < n_seg && cnt) {
+        unsigned long long o = base + running + before + (incl - cnt);
+        for (unsigned long long i = lo; i < hi; i++)
+          if (g.get() <= keep_max) {
+            if (o < row_cap) {
+              s1[o] = site;
+              const uint32_t c2 = first + (uint32_t)i;
+              s2[o] = cs ? cs[c2] : c2;
+            }
+            o++;
+          }
+      }
+      running += total;
     }
-    if (!mode) counts[c1 - c_lo] = kept;
+    if (!mode && tid == 0) counts[c1 - c_lo] = running;
   }
 }
 

@@ -11,10 +11,9 @@ __global__ void expand_window_kernel(const unsigned long long *row_off, const ui
                                      unsigned long long row_lo, unsigned long long n, uint32_t *s1, uint32_t *s2);
 __global__ void fill_rows_kernel(SiteTable T, PairChunk C);
 __global__ void taus_sample_kernel(const unsigned long long *site_seeds, const uint32_t *cs, const uint32_t *cw_end,
-                                   uint32_t c_lo, uint32_t c_hi, double rnd_sample, int mode,
-                                   unsigned long long *counts, const unsigned long long *row_off,
-                                   unsigned long long row_base, unsigned long long row_cap, uint32_t *s1,
-                                   uint32_t *s2);
+                                   uint32_t c_lo, uint32_t c_hi, uint32_t keep_max, int mode, unsigned long long *counts,
+                                   const unsigned long long *row_off, unsigned long long row_base, unsigned long long row_cap,
+                                   uint32_t *s1, uint32_t *s2, const uint32_t *jump);
 __global__ void decay_bins_kernel(const ngsld_pair_row *rows, unsigned long long n, double bin_size,
                                   unsigned long long n_bins, ngsld_decay_bin *bins, unsigned long long *outside);
 __global__ void prune_edges_kernel(const ngsld_pair_row *rows, unsigned long long n, ngsld_prune_params q, double precision,

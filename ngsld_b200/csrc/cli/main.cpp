@@ -242,6 +242,100 @@ int main(int argc, char **argv) {
   if (!prune_mode && !shards && hl && !write_all(out_fd, header, (size_t)hl, seekable ? 0 : -1)) die(fn, "cannot write output!");
 
   const double t_start = wall_s();
+  // ---- in the background from the first moment: CUDA start-up, one context per GPU (seconds on an 8-GPU box) ----
+  int n_dev = 0, n_gpu = 0;
+  std::vector<ngsld_ctx *> ctx;
+  std::vector<int> create_rc;
+  std::mutex mu;                 // guards everything the GPU, writer and allocator threads share
+  std::condition_variable cv;
+  bool devices_known = false;
+  std::thread boot([&]() {
+    const int nd = ngsld_device_count();
+    const int ng = nd < 1 ? 0 : (o.gpu_n > 0 ? std::min(o.gpu_n, nd) : nd);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      n_dev = nd;
+      n_gpu = ng;
+      ctx.assign(ng, nullptr);
+      create_rc.assign(ng, 0);
+      devices_known = true;
+    }
+    cv.notify_all();
+    std::vector<std::thread> th;
+    for (int g = 0; g < ng; g++) th.emplace_back([&, g]() { create_rc[g] = ngsld_create(&ctx[g], g); });
+    for (auto &t : th) t.join();
+  });
+  // positions first (small file): the longest label bounds the length of a TSV row, which sizes the slab buffers, and those
+  // are page-locked in the background while the genotypes are read.  A failure is reported where the reference reports it.
+  std::vector<double> pos_dist;
+  std::vector<const char *> label_ptr;
+  char *label_blob = nullptr;
+  std::string pos_error;
+  uint32_t max_label_len = 6;  // "(null)"
+  if (o.in_pos) {
+    pos_dist.resize(o.n_sites);
+    if (ngsld_load_positions(o.in_pos, o.in_pos_header, o.n_sites, pos_dist.data(), &label_blob, NULL) != NGSLD_OK) {
+      pos_error = ngsld_last_error(NULL);
+    } else {
+      label_ptr.resize(o.n_sites);
+      const char *p = label_blob;
+      max_label_len = 1;
+      for (uint64_t s = 0; s < o.n_sites; s++) {
+        label_ptr[s] = p;
+        const size_t len = strlen(p);
+        max_label_len = std::max<uint32_t>(max_label_len, (uint32_t)len);
+        p += len + 1;
+      }
+    }
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&]() { return devices_known; });
+  }
+  // ---- slab buffers (see below): sized now, page-locked in the background ----
+  const uint64_t row_bound = o.out_bin ? sizeof(ngsld_pair_row) : ngsld_tsv_row_bound_for(max_label_len, o.extend_out);
+  uint64_t buf_bytes = (n_gpu > 2 ? 256ull : 512ull) << 20;  // page-locking costs ~0.4 s per GB, and again at exit
+  if (const char *e = getenv("NGSLD_CLI_BUF_MB"))
+    if (atoll(e) > 0) buf_bytes = (uint64_t)atoll(e) << 20;
+  uint64_t rows_per_slab = std::max<uint64_t>(1, std::min<uint64_t>(16ull << 20, buf_bytes / row_bound));
+  if (const char *e = getenv("NGSLD_CLI_SLAB_ROWS"))  // tests: force many small slabs
+    if (atoll(e) > 0) rows_per_slab = (uint64_t)atoll(e);
+  // a slab holds its share of the rows (at most rows_per_slab) plus at most the rows of one first site
+  const uint64_t cap = std::max<uint64_t>((rows_per_slab + o.n_sites + 1) * row_bound, 4096);
+  // one pwrite() stream into the page cache moves ~3.5 GB/s; a GPU produces ~4 GB/s of text
+  const int n_writers = shards ? std::max(2, std::min(2 * n_gpu, 16)) : seekable ? 2 : 1;
+  const int n_bufs = n_gpu + n_writers + 1;
+  struct Buf {
+    char *p = nullptr;
+    bool pinned = false;
+  };
+  std::vector<Buf> bufs(n_bufs);
+  std::vector<int> free_bufs;
+  bool alloc_failed = false, failed = false, write_failed = false;
+  const double t_alloc0 = wall_s();
+  double t_alloc = 0;
+  std::vector<std::thread> allocators;
+  if (!prune_mode && n_gpu > 0)
+    for (int k = 0; k < n_bufs; k++)
+      allocators.emplace_back([&, k]() {
+        void *q = nullptr;
+        Buf b;
+        if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
+          b.p = (char *)q;
+          b.pinned = true;
+        } else {
+          b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
+        }
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          bufs[k] = b;
+          if (b.p) free_bufs.push_back(k);
+          else alloc_failed = failed = true;
+          t_alloc = wall_s() - t_alloc0;
+        }
+        cv.notify_all();
+      });
+
   if (o.verbose >= 1) fprintf(stderr, "> Reading data from file...\n");
   std::vector<double> cells((size_t)o.n_sites * o.n_ind * 3);
   int log_cells = 0;
@@ -268,24 +362,16 @@ int main(int argc, char **argv) {
   const double t_prep = wall_s();
 
   if (o.verbose >= 1) fprintf(stderr, "==> Getting sites coordinates\n");
-  std::vector<double> pos_dist;
-  std::vector<const char *> label_ptr;
-  char *label_blob = nullptr;
-  if (o.in_pos) {
-    pos_dist.resize(o.n_sites);
-    if (ngsld_load_positions(o.in_pos, o.in_pos_header, o.n_sites, pos_dist.data(), &label_blob, NULL) != NGSLD_OK)
-      die_lib("read_dist");
-    label_ptr.resize(o.n_sites);
-    const char *p = label_blob;
-    for (uint64_t s = 0; s < o.n_sites; s++) {
-      label_ptr[s] = p;
-      p += strlen(p) + 1;
-    }
+  if (!pos_error.empty()) {  // (read early, reported here)
+    fflush(stdout);
+    if (pos_error[0] == '[') fprintf(stderr, "\n=====\nERROR: %s\n=====\n\n", pos_error.c_str());
+    else fprintf(stderr, "\n=====\nERROR: [read_dist] %s\n=====\n\n", pos_error.c_str());
+    perror("\t");
+    exit(-1);
   }
 
-  const int n_dev = ngsld_device_count();
+  boot.join();
   if (n_dev < 1) die(fn, "no CUDA device available (this build has no CPU path)!");
-  const int n_gpu = o.gpu_n > 0 ? std::min(o.gpu_n, n_dev) : n_dev;
   if (o.verbose >= 1) fprintf(stderr, "==> Launching threads...\n");
 
   ngsld_scan_params P;
@@ -300,10 +386,9 @@ int main(int argc, char **argv) {
   P.strict = o.gpu_strict;
 
   // ---- site table: one upload from the host, then passed on GPU to GPU (NVLink) in a doubling tree ----
-  std::vector<ngsld_ctx *> ctx(n_gpu, nullptr);
   const bool host_upload_all = getenv("NGSLD_CLI_HOST_UPLOAD") && atoi(getenv("NGSLD_CLI_HOST_UPLOAD"));
   auto from_host = [&](int g) -> int {
-    int r = ngsld_create(&ctx[g], g);
+    int r = create_rc[g];
     if (r) return r;
     if (o.gpu_prep)
       r = ngsld_set_sites_raw(ctx[g], cells.data(), o.n_sites, o.n_ind, o.in_logscale, log_cells, o.ignore_miss_data, o.call_geno,
@@ -334,7 +419,7 @@ int main(int argc, char **argv) {
         std::vector<std::thread> th;
         for (int g = have; g < std::min(n_gpu, 2 * have); g++)
           th.emplace_back([&, g, have]() {
-            rcs[g] = ngsld_create(&ctx[g], g);
+            rcs[g] = create_rc[g];
             if (!rcs[g]) rcs[g] = ngsld_share_sites(ctx[g], ctx[g - have]);
           });
         for (auto &t : th) t.join();
@@ -447,32 +532,14 @@ int main(int argc, char **argv) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to plan the pair scan!");
   }
-  const uint64_t row_bound = o.out_bin ? sizeof(ngsld_pair_row) : ngsld_tsv_row_bound(ctx[0], o.extend_out);
-  uint64_t buf_bytes = 512ull << 20;  // per slab buffer; a scan drains its chunk pipeline at the end, so slabs stay long
-  if (const char *e = getenv("NGSLD_CLI_BUF_MB"))
-    if (atoll(e) > 0) buf_bytes = (uint64_t)atoll(e) << 20;
-  uint64_t rows_per_slab = std::max<uint64_t>(1, std::min<uint64_t>(16ull << 20, buf_bytes / row_bound));
-  if (const char *e = getenv("NGSLD_CLI_SLAB_ROWS"))  // tests: force many small slabs
-    if (atoll(e) > 0) rows_per_slab = (uint64_t)atoll(e);
   const int n_slabs = (int)std::min<uint64_t>(std::max<uint64_t>((total_rows + rows_per_slab - 1) / rows_per_slab, (uint64_t)n_gpu), 1u << 20);
   std::vector<uint64_t> bounds(n_slabs + 1);
   if (ngsld_partition(ctx[0], &P, n_slabs, bounds.data()) != NGSLD_OK) {
     fprintf(stderr, "%s\n", ngsld_last_error(ctx[0]));
     die(fn, "failed to partition the pair space!");
   }
-  // a slab holds its share of the rows plus at most the rows of one first site
-  const uint64_t slab_rows_max = std::min<uint64_t>(total_rows, (total_rows + n_slabs - 1) / n_slabs + o.n_sites + 1);
-  const uint64_t cap = std::max<uint64_t>(slab_rows_max * row_bound, 4096);
 
   if (o.verbose >= 1) fprintf(stderr, "==> Waiting for all threads to finish...\n");
-  // one pwrite() stream into the page cache moves ~3.5 GB/s; a GPU produces ~4 GB/s of text
-  const int n_writers = shards ? std::max(2, std::min(2 * n_gpu, 16)) : seekable ? 2 : 1;
-  const int n_bufs = n_gpu + n_writers + 1;
-  struct Buf {
-    char *p = nullptr;
-    bool pinned = false;
-  };
-  std::vector<Buf> bufs(n_bufs);
   struct Slab {
     int buf = -1;
     uint64_t bytes = 0, rows = 0;
@@ -481,14 +548,9 @@ int main(int argc, char **argv) {
     std::string spill;          // only when a slab outgrew its buffer (values the host formatter had to print)
   };
   std::vector<Slab> slab(n_slabs);
-  std::mutex mu;
-  std::condition_variable cv;
-  std::vector<int> free_bufs;
-  bool alloc_failed = false;
   int next_slab = 0, next_off = 0, written = 0;
   std::deque<int> ready;  // slabs that can be written now: formatted and (one file) with their offset known
   off_t cursor = shards ? 0 : hl;
-  bool failed = false, write_failed = false;
   struct PerGpu {
     uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0, cells = 0, cell_pairs = 0, resid = 0;
     double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0, s_scan = 0, s_wait = 0;
@@ -499,31 +561,6 @@ int main(int argc, char **argv) {
     double s_write = 0;
   };
   std::vector<PerWriter> wacc(n_writers);
-
-  // The slab buffers are page-locked in the background (that is kernel work per page, ~0.2 s per buffer): the GPUs start on
-  // the first ones while the rest are still being allocated.
-  const double t_alloc0 = wall_s();
-  double t_alloc = 0;
-  std::vector<std::thread> allocators;
-  for (int k = 0; k < n_bufs; k++)
-    allocators.emplace_back([&, k]() {
-      void *q = nullptr;
-      Buf b;
-      if (ngsld_alloc_host(&q, cap) == NGSLD_OK) {
-        b.p = (char *)q;
-        b.pinned = true;
-      } else {
-        b.p = (char *)malloc(cap);  // pageable: the copies are staged by the driver, everything else works the same
-      }
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        bufs[k] = b;
-        if (b.p) free_bufs.push_back(k);
-        else alloc_failed = failed = true;
-        t_alloc = wall_s() - t_alloc0;
-      }
-      cv.notify_all();
-    });
 
   std::vector<std::thread> writers;
   for (int w = 0; w < n_writers; w++)
@@ -664,7 +701,7 @@ int main(int argc, char **argv) {
     for (int w = 0; w < n_writers; w++)
       fprintf(stderr, "[writer %d] %.2f GB in %.2f s of %s = %.2f GB/s\n", w, wacc[w].bytes / 1e9, wacc[w].s_write,
               shards ? "write to slab files" : seekable ? "pwrite" : "write", wacc[w].s_write > 0 ? wacc[w].bytes / 1e9 / wacc[w].s_write : 0.0);
-    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, all of them allocated %.2f s into the scan)\n",
+    fprintf(stderr, "[time] read %.2f s, prepare (host) %.2f s, positions + site table to %d GPU(s) %.2f s (%s), scan %.2f s, writers done %.2f s after the scan; %lu rows, %.2f GB of text, %.0f rows/s over scan + write, %d slab buffers of %.0f MB (%s, the last one ready %.2f s after the positions were read)\n",
             t_read - t_start, t_prep - t_read, n_gpu, t_upload - t_prep, host_upload_all || n_gpu == 1 ? "from the host" : "one upload, then GPU to GPU",
             t_scan1 - t_scan0, t_done - t_scan1, all_pairs, (double)(cursor - (shards ? 0 : hl)) / 1e9, all_pairs / std::max(t_done - t_scan0, 1e-9), n_bufs, cap / 1e6,
             bufs[0].pinned ? "page-locked" : "pageable", t_alloc);

@@ -95,6 +95,7 @@ struct ngsld_ctx {
   bool cell_possible = false;  // palettes exist (NGSLD_EM_PATH=cell can force the kernel)
   double cell_mean = 0, cell_uncoded_frac = 0;
   uint32_t cell_p995 = 0;      // 99.5 % of the sampled pairs have at most this many cells
+  uint32_t cell_kstride = NGSLD_KMAX;  // largest site palette, rounded up to 8: row length of the joint-class tables
   // positions / labels
   bool have_pos = false;
   std::vector<double> h_cum;
@@ -110,6 +111,7 @@ struct ngsld_ctx {
   // plan buffers
   uint32_t *d_cs = nullptr, *d_cw_end = nullptr;
   unsigned long long *d_row_off = nullptr, *d_seeds = nullptr, *d_counts = nullptr;
+  uint32_t *d_taus_jump = nullptr;  // jump-ahead tables of the sampling generator (hostprep::taus_jump_tables)
   uint2 *d_tiles = nullptr;
   size_t cap_compact = 0, cap_tiles = 0;
   DevCounters *d_ctr = nullptr;
@@ -231,10 +233,11 @@ int alloc_site_buffers(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind, bool with
     CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
     CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * n_pad * sizeof(uint64_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * n_pad * sizeof(uint16_t)));
+    // (one spare row / entry behind the tables: the r2_ExpG loop requests the operands of individual i + 1 unconditionally)
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * (n_pad + 1) * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * (n_pad + 1) * sizeof(uint16_t)));
     CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_pad * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_ratio, (n_pad + 1) * sizeof(uint64_t)));
     if (n_ind < 65536) {  // joint-class counters are 16 bits wide
       CUDA_TRY(c, cudaMalloc(&c->d_cls, n_sites * n_cpad));
       CUDA_TRY(c, cudaMalloc(&c->d_pal, n_sites * (size_t)NGSLD_KMAX * 3 * sizeof(double)));
@@ -363,6 +366,13 @@ int make_plan(const PlanInput &in, uint64_t s1_lo, uint64_t s1_hi, const ngsld_s
   return NGSLD_OK;
 }
 
+// A candidate pair is kept iff !(get() / 2^32 > rnd_sample) (reference ngsLD.cpp:277, gen_func.cpp:117-119), i.e. iff
+// get() <= floor(rnd_sample * 2^32): both scalings by 2^32 are exact in double.  Only used for rnd_sample < 1.
+uint32_t keep_max_of(double rnd_sample) {
+  const double x = floor(rnd_sample * 4294967296.0);
+  return x >= 4294967295.0 ? 4294967295u : (uint32_t)x;
+}
+
 // Exact prefix sums of the inter-site gaps: every finite gap must be a non-negative integer and the total below
 // 2^53, so that cum[s2]-cum[s1] equals the reference's running double sum (ngsLD.cpp:241) bit for bit.  A +inf gap
 // (chromosome change, read_data.cpp:209) starts a new segment.  Returns NULL or the reason for rejection.
@@ -457,14 +467,19 @@ int upload_plan(ngsld_ctx *c, Plan &pl, const ngsld_scan_params &P) {
     CUDA_TRY(c, cudaMalloc(&c->d_seeds, c->n_sites * sizeof(unsigned long long)));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_seeds, seeds.data(), c->n_sites * 8, cudaMemcpyHostToDevice, c->s_main));
     c->stats.h2d_bytes += c->n_sites * 8;
+    if (!c->d_taus_jump) {
+      std::vector<uint32_t> jump((size_t)hostprep::TAUS_JUMP_LEVELS * 3 * 32);
+      hostprep::taus_jump_tables(jump.data());
+      CUDA_TRY(c, cudaMalloc(&c->d_taus_jump, jump.size() * sizeof(uint32_t)));
+      CUDA_TRY(c, cudaMemcpy(c->d_taus_jump, jump.data(), jump.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     const uint32_t span = pl.c_hi - pl.c_lo;
     std::vector<unsigned long long> counts(span);
     if (span) {
-      const int threads = 128;
-      const unsigned blocks = (unsigned)std::min<uint64_t>((span + threads - 1) / threads, 65535u * 16u);
-      aux::taus_sample_kernel<<<blocks, threads, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end,
-                                                                 pl.c_lo, pl.c_hi, P.rnd_sample, 0, c->d_counts, nullptr, 0,
-                                                                 0, nullptr, nullptr);
+      const unsigned blocks = (unsigned)std::min<uint64_t>(span, (uint64_t)c->sm_count * 32);
+      aux::taus_sample_kernel<<<blocks, 256, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end, pl.c_lo,
+                                                             pl.c_hi, keep_max_of(P.rnd_sample), 0, c->d_counts, nullptr, 0, 0,
+                                                             nullptr, nullptr, c->d_taus_jump);
       c->stats.n_launches++;
       CUDA_TRY(c, cudaGetLastError());
       CUDA_TRY(c, cudaMemcpyAsync(counts.data(), c->d_counts, span * 8ull, cudaMemcpyDeviceToHost, c->s_main));
@@ -575,6 +590,7 @@ int launch_cell(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
   A.tcap = ch.cell_tcap;
   A.ignore_miss = ignore_miss;
   A.fuse_pearson = ch.cell_fuse ? 1 : 0;
+  A.kstride = c->cell_kstride;
   void *args[] = {&Tt, &Cc, &A, &ctr};
   const unsigned long long want = (C.n_pairs + 32ull * emcell::WARPS_PER_CTA - 1) / (32ull * emcell::WARPS_PER_CTA);
   const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_cell);
@@ -604,8 +620,8 @@ int choose_cell(ngsld_ctx *c, EmChoice &ch) {
   tcap = std::max<uint32_t>(tcap, 64);  // room for the odd pair beyond the sampled percentile
   if (const char *e = getenv("NGSLD_CELL_TCAP")) tcap = ((uint32_t)atoi(e) + 63u) & ~63u;
   // at least two CTAs per SM: shrink the tail if it does not fit (pairs beyond it go to the dense kernel)
-  while (tcap > 0 && 2 * (emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap) + 1024) > (size_t)c->smem_optin) tcap -= 64;
-  const size_t smem = emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap);
+  while (tcap > 0 && 2 * (emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap, c->cell_kstride) + 1024) > (size_t)c->smem_optin) tcap -= 64;
+  const size_t smem = emcell::WARPS_PER_CTA * emcell::warp_smem_bytes(r, tcap, c->cell_kstride);
   if (smem + 1024 > (size_t)c->smem_optin) return NGSLD_OK;
   int occ = 0;
   for (const void *fn : {v->fn, v->fn_fused}) {
@@ -697,9 +713,10 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
   const uint32_t ca = row_owner(pl, r0), cb = row_owner(pl, r1 - 1) + 1;
   if (pl.sampled) {
     const uint32_t span = cb - ca;
-    const unsigned sb = (unsigned)std::min<uint64_t>((span + 127) / 128, 65535u * 16u);
-    aux::taus_sample_kernel<<<sb, 128, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end, ca, cb,
-                                                       P.rnd_sample, 1, nullptr, c->d_row_off, r0, n, b.d_s1, b.d_s2);
+    const unsigned sb = (unsigned)std::min<uint64_t>(span, (uint64_t)c->sm_count * 32);
+    aux::taus_sample_kernel<<<sb, 256, 0, c->s_main>>>(c->d_seeds, pl.identity ? nullptr : c->d_cs, c->d_cw_end, ca, cb,
+                                                       keep_max_of(P.rnd_sample), 1, nullptr, c->d_row_off, r0, n, b.d_s1, b.d_s2,
+                                                       c->d_taus_jump);
   } else {
     aux::expand_window_kernel<<<gblocks, threads, 0, c->s_main>>>(c->d_row_off, pl.identity ? nullptr : c->d_cs,
                                                                    pl.n_compact, r0, n, b.d_s1, b.d_s2);
@@ -1106,6 +1123,7 @@ void ngsld_destroy(ngsld_ctx *c) {
   dfree(c->d_row_off);
   dfree(c->d_seeds);
   dfree(c->d_counts);
+  dfree(c->d_taus_jump);
   dfree(c->d_tiles);
   dfree(c->d_ctr);
   dfree(c->d_decay_bins);
@@ -1187,10 +1205,11 @@ int finish_sites(ngsld_ctx *c, const double *host_expg) {
   c->cell_p995 = 0;
   if (c->d_cls && n_sites >= 2) {
     const unsigned pblocks = (unsigned)std::min<uint64_t>((n_sites + 3) / 4, (uint64_t)c->sm_count * 16);
-    emcell::build_palette_kernel<<<pblocks, emcell::CTA_THREADS, 0, c->s_main>>>(
-        c->d_gl, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad, (uint32_t)n_cpad, c->d_cls, c->d_pal, c->d_pal_k, c->d_pal_miss);
     const size_t stat_bytes = 3 * sizeof(unsigned long long) + 132 * sizeof(unsigned int);
     CUDA_TRY(c, cudaMemsetAsync(c->d_cell_stats, 0, stat_bytes, c->s_main));
+    emcell::build_palette_kernel<<<pblocks, emcell::CTA_THREADS, 0, c->s_main>>>(
+        c->d_gl, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad, (uint32_t)n_cpad, c->d_cls, c->d_pal, c->d_pal_k, c->d_pal_miss,
+        reinterpret_cast<unsigned int *>(c->d_cell_stats + 3) + 130);  // hist[130]: largest palette
     const uint32_t n_samples = 4096;
     SiteTable T = site_table(c);
     emcell::cell_stats_kernel<<<c->sm_count * 2, emcell::CTA_THREADS, 0, c->s_main>>>(
@@ -1205,6 +1224,7 @@ int finish_sites(ngsld_ctx *c, const double *host_expg) {
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
     const unsigned long long coded = hs.n - hs.uncoded;
     c->cell_uncoded_frac = hs.n ? (double)hs.uncoded / (double)hs.n : 1.0;
+    c->cell_kstride = std::min<uint32_t>(NGSLD_KMAX, std::max<uint32_t>(8, (hs.hist[130] + 7u) & ~7u));
     if (coded) {
       c->cell_mean = (double)hs.sum / (double)coded;
       unsigned long long acc = 0;
@@ -1557,6 +1577,10 @@ uint64_t ngsld_tsv_row_bound(const ngsld_ctx *c, int extend_out) {
   return fmt::slot_bytes(c ? c->max_label_len : 6, extend_out != 0);
 }
 
+uint64_t ngsld_tsv_row_bound_for(uint32_t max_label_len, int extend_out) {
+  return fmt::slot_bytes(max_label_len ? max_label_len : 1, extend_out != 0);
+}
+
 int ngsld_alloc_host(void **p, size_t bytes) {
   if (!p) return NGSLD_E_INVALID;
   *p = nullptr;
@@ -1609,7 +1633,7 @@ int ngsld_share_sites(ngsld_ctx *dst, const ngsld_ctx *src) {
   CUDA_TRY(c, peer(c->d_dx_sig, src->d_dx_sig, n * n_pad * 8));
   CUDA_TRY(c, peer(c->d_dx_se, src->d_dx_se, n * n_pad * 2));
   CUDA_TRY(c, peer(c->d_seg, src->d_seg, n * 4));
-  CUDA_TRY(c, peer(c->d_ratio, src->d_ratio, n_pad * 8));
+  CUDA_TRY(c, peer(c->d_ratio, src->d_ratio, (n_pad + 1) * 8));
   if (c->d_cls && src->d_cls) {
     CUDA_TRY(c, peer(c->d_cls, src->d_cls, n * n_cpad));
     CUDA_TRY(c, peer(c->d_pal, src->d_pal, n * (size_t)NGSLD_KMAX * 24));
@@ -1642,6 +1666,7 @@ int ngsld_share_sites(ngsld_ctx *dst, const ngsld_ctx *src) {
   c->cell_mean = src->cell_mean;
   c->cell_uncoded_frac = src->cell_uncoded_frac;
   c->cell_p995 = src->cell_p995;
+  c->cell_kstride = src->cell_kstride;
   CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   memset(&c->stats, 0, sizeof c->stats);
   c->stats.h2d_bytes = 0;

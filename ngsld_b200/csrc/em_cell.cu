@@ -6,7 +6,7 @@ namespace emcell {
 
 __global__ void __launch_bounds__(CTA_THREADS) build_palette_kernel(const double *gl, uint32_t n_sites, uint32_t n_ind,
                                                                     uint32_t n_pad, uint32_t n_cpad, uint8_t *cls, double *pal,
-                                                                    uint8_t *pal_k, uint64_t *pal_miss) {
+                                                                    uint8_t *pal_k, uint64_t *pal_miss, unsigned int *max_k) {
   __shared__ unsigned long long ps[WARPS_PER_CTA][3][NGSLD_KMAX];  // the palette being built, as bit patterns
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long(*p)[NGSLD_KMAX] = ps[warp];
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(CTA_THREADS) build_palette_kernel(const double
     if (lane == 0) {
       pal_k[s] = (uint8_t)k;
       pal_miss[s] = miss;
+      atomicMax(max_k, k);  // the largest palette sizes the joint-class tables of the EM kernel
     }
     __syncwarp();  // the next site overwrites the shared palette
   }
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(CTA_THREADS) cell_stats_kernel(SiteTable T, ui
   __shared__ __align__(16) uint16_t all_bins[WARPS_PER_CTA][NBINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint16_t *bins = all_bins[warp];
-  wipe_bins(bins, lane);
+  wipe_bins(bins, NGSLD_KMAX, lane);
   for (uint32_t j = blockIdx.x * WARPS_PER_CTA + warp; j < n_samples; j += gridDim.x * WARPS_PER_CTA) {
     const uint32_t s1 = mix32(2u * j + 1u) % T.n_sites;
     uint32_t s2 = mix32(2u * j + 2u) % T.n_sites;
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(CTA_THREADS) cell_stats_kernel(SiteTable T, ui
       continue;
     }
     uint32_t used = 0;
-    const uint32_t n = joint_classes(T, s1, s2, ignore_miss != 0, bins, nullptr, 0, used, lane);
-    wipe_bins(bins, lane);
+    const uint32_t n = joint_classes(T, s1, s2, ignore_miss != 0, bins, NGSLD_KMAX, nullptr, 0, used, lane);
+    wipe_bins(bins, NGSLD_KMAX, lane);
     if (lane == 0) {
       atomicAdd(&out[0], (unsigned long long)n);
       atomicAdd(&out[1], 1ull);

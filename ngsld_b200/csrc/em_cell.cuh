@@ -14,7 +14,7 @@
 //
 // Per site, build_palette_kernel lists the distinct triples (the "palette", at most NGSLD_KMAX entries, bitwise
 // equality) and codes every individual as one byte.  Per pair, a warp
-//   1. counts the joint classes (c1[i], c2[i]) of the individuals in a 64 x 64 table of 16-bit counters in shared
+//   1. counts the joint classes (c1[i], c2[i]) of the individuals in a K x K table of 16-bit counters in shared
 //      memory (lanes with equal keys are combined with match.any, so no two lanes touch the same counter), noting every
 //      counter that becomes non-zero in a list: the pair's cells;
 //   2. loads the cells -- palette triples + weight -- into registers (R per lane; cells beyond 32 R go to a shared-
@@ -35,7 +35,7 @@ namespace emcell {
 
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
-constexpr int NBINS = NGSLD_KMAX * NGSLD_KMAX;
+constexpr int NBINS = NGSLD_KMAX * NGSLD_KMAX;  // largest joint-class table (the kernels size theirs from the data)
 
 using emfast::Ind;
 using emfast::estep;
@@ -45,25 +45,27 @@ struct CellArgs {
   uint32_t tcap;      // cells a warp can hold in shared memory beyond its 32 R register cells (multiple of 64)
   int ignore_miss;    // --ignore_miss_data: individuals whose class is flat at either site are left out
   int fuse_pearson;   // compute r2_ExpG in this kernel
+  uint32_t kstride;   // row length of the joint-class table: the largest palette of the data set, rounded up to 8
 };
 
 // shared memory of one warp: joint-class counters | cell keys | tail cells (7 doubles each, structure of arrays)
-__host__ __device__ inline size_t warp_smem_bytes(int r, uint32_t tcap) {
+__host__ __device__ inline size_t bins_bytes(uint32_t kstride) { return ((size_t)kstride * kstride * 2 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t warp_smem_bytes(int r, uint32_t tcap, uint32_t kstride) {
   const size_t keys = ((size_t)(32 * r + tcap) * 2 + 15) & ~(size_t)15;
-  return (size_t)NBINS * 2 + keys + (size_t)tcap * 7 * 8;
+  return bins_bytes(kstride) + keys + (size_t)tcap * 7 * 8;
 }
 
-__device__ __forceinline__ void wipe_bins(uint16_t *bins, int lane) {
+__device__ __forceinline__ void wipe_bins(uint16_t *bins, uint32_t kstride, int lane) {
   uint4 *b = reinterpret_cast<uint4 *>(bins);
-  for (int k = lane; k < NBINS * 2 / 16; k += 32) b[k] = make_uint4(0, 0, 0, 0);
+  for (int k = lane; k < (int)(bins_bytes(kstride) / 16); k += 32) b[k] = make_uint4(0, 0, 0, 0);
   __syncwarp();
 }
 
-// Joint classes of a pair.  bins must be all zero on entry; on return bins[key] = individuals with joint class key
-// (key = c1 * 64 + c2), keys[0 .. min(n_cells, cap)) = the distinct keys in order of first appearance, n_used =
-// individuals counted.  Returns n_cells (if it exceeds cap the caller has to wipe the whole table).
+// Joint classes of a pair.  bins must be all zero on entry; on return bins[c1 * kstride + c2] = individuals with classes
+// (c1, c2), keys[0 .. min(n_cells, cap)) = the distinct (c1 << 8 | c2) in order of first appearance, n_used = individuals
+// counted.  Returns n_cells (if it exceeds cap the caller has to wipe the whole table).
 __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s1, uint32_t s2, bool ign, uint16_t *bins,
-                                                  uint16_t *keys, uint32_t cap, uint32_t &n_used, int lane) {
+                                                  uint32_t kstride, uint16_t *keys, uint32_t cap, uint32_t &n_used, int lane) {
   const uint8_t *c1 = T.cls + (size_t)s1 * T.n_cpad, *c2 = T.cls + (size_t)s2 * T.n_cpad;
   const uint64_t miss1 = ign ? T.pal_miss[s1] : 0ull, miss2 = ign ? T.pal_miss[s2] : 0ull;
   const uint32_t lt = (1u << lane) - 1u;
@@ -80,13 +82,14 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
       const uint32_t a = (w1 >> (8 * e)) & 255u, b = (w2 >> (8 * e)) & 255u;
       bool valid = i0 + e < T.n_ind;
       if (valid && ign) valid = !((((miss1 >> a) | (miss2 >> b)) & 1ull) != 0);
-      const uint32_t key = valid ? (a << 6 | b) : 0xffffu;
+      const uint32_t key = valid ? (a << 8 | b) : 0xffffffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       const bool lead = valid && (__ffs(peers) - 1 == lane);
       bool fresh = false;
       if (lead) {
-        const uint32_t old = bins[key];
-        bins[key] = (uint16_t)(old + __popc(peers));
+        const uint32_t bin = a * kstride + b;
+        const uint32_t old = bins[bin];
+        bins[bin] = (uint16_t)(old + __popc(peers));
         fresh = old == 0;
       }
       const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
@@ -113,13 +116,16 @@ __device__ __forceinline__ void cell_default(Cell &c) {  // an empty slot: weigh
   c.w = 0.0;
 }
 
-__device__ __forceinline__ void cell_load(Cell &c, const SiteTable &T, uint32_t s1, uint32_t s2, uint32_t key, uint16_t *bins) {
-  const double *pa = T.pal + ((size_t)s1 * NGSLD_KMAX + (key >> 6)) * 3;
-  const double *pb = T.pal + ((size_t)s2 * NGSLD_KMAX + (key & 63u)) * 3;
+__device__ __forceinline__ void cell_load(Cell &c, const SiteTable &T, uint32_t s1, uint32_t s2, uint32_t key, uint16_t *bins,
+                                          uint32_t kstride) {
+  const uint32_t a = key >> 8, b = key & 255u;
+  const double *pa = T.pal + ((size_t)s1 * NGSLD_KMAX + a) * 3;
+  const double *pb = T.pal + ((size_t)s2 * NGSLD_KMAX + b) * 3;
   c.g.p0 = __ldg(pa); c.g.p1 = __ldg(pa + 1); c.g.p2 = __ldg(pa + 2);
   c.g.q0 = __ldg(pb); c.g.q1 = __ldg(pb + 1); c.g.q2 = __ldg(pb + 2);
-  c.w = (double)bins[key];
-  bins[key] = 0;  // every counter in use belongs to exactly one cell: the table is clean again after the loads
+  const uint32_t bin = a * kstride + b;
+  c.w = (double)bins[bin];
+  bins[bin] = 0;  // every counter in use belongs to exactly one cell: the table is clean again after the loads
 }
 
 __device__ __forceinline__ void cell_step(const double f0, const double f1, const double f2, const double f3, const Cell &c,
@@ -202,11 +208,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t cap = 32u * R + A.tcap;
-  unsigned char *mine = dyn_smem + (size_t)warp * warp_smem_bytes(R, A.tcap);
+  unsigned char *mine = dyn_smem + (size_t)warp * warp_smem_bytes(R, A.tcap, A.kstride);
   uint16_t *bins = reinterpret_cast<uint16_t *>(mine);
-  uint16_t *keys = bins + NBINS;
-  double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap) - (size_t)A.tcap * 56);
-  wipe_bins(bins, lane);
+  uint16_t *keys = reinterpret_cast<uint16_t *>(mine + bins_bytes(A.kstride));
+  double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap, A.kstride) - (size_t)A.tcap * 56);
+  wipe_bins(bins, A.kstride, lane);
   const bool ign = A.ignore_miss != 0;
   unsigned long long my_passes = 0, my_cell_passes = 0, my_cells = 0, my_pairs = 0, my_resid = 0;
 
@@ -235,9 +241,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       uint32_t n_cells = 0, n_used = T.n_ind;
       bool mine_ok = k1 != 0 && k2 != 0;
       if (mine_ok) {
-        n_cells = joint_classes(T, s1, s2, ign, bins, keys, cap, n_used, lane);
+        n_cells = joint_classes(T, s1, s2, ign, bins, A.kstride, keys, cap, n_used, lane);
         if (n_cells > cap) {
-          wipe_bins(bins, lane);
+          wipe_bins(bins, A.kstride, lane);
           mine_ok = false;
         }
       }
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       for (int r = 0; r < R; r++) {
         const uint32_t slot = (uint32_t)lane + 32u * r;
         cell_default(g[r]);
-        if (slot < n_cells) cell_load(g[r], T, s1, s2, keys[slot], bins);
+        if (slot < n_cells) cell_load(g[r], T, s1, s2, keys[slot], bins, A.kstride);
       }
       const uint32_t n_tail = n_cells > 32u * R ? n_cells - 32u * R : 0u;
       const uint32_t n_tail_pad = (n_tail + 63u) & ~63u;  // two cells per lane and trip: filled up with empty cells
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       for (uint32_t t = lane; t < n_tail_pad; t += 32u) {
         Cell c;
         cell_default(c);
-        if (t < n_tail) cell_load(c, T, s1, s2, keys[32u * R + t], bins);
+        if (t < n_tail) cell_load(c, T, s1, s2, keys[32u * R + t], bins, A.kstride);
         tail[0 * A.tcap + t] = c.g.p0; tail[1 * A.tcap + t] = c.g.p1; tail[2 * A.tcap + t] = c.g.p2;
         tail[3 * A.tcap + t] = c.g.q0; tail[4 * A.tcap + t] = c.g.q1; tail[5 * A.tcap + t] = c.g.q2;
         tail[6 * A.tcap + t] = c.w;
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
 // of every individual, and which classes are "missing data".  A site with more than NGSLD_KMAX distinct triples gets
 // pal_k = 0 and is not coded.
 __global__ void __launch_bounds__(CTA_THREADS) build_palette_kernel(const double *gl, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad, uint32_t n_cpad,
-                                     uint8_t *cls, double *pal, uint8_t *pal_k, uint64_t *pal_miss);
+                                     uint8_t *cls, double *pal, uint8_t *pal_k, uint64_t *pal_miss, unsigned int *max_k);
 
 // n_samples pseudo-random pairs: out[0] = sum of cells, out[1] = pairs sampled, out[2] = pairs with an uncoded site,
 // hist[b] = pairs with 32 b <= cells < 32 (b + 1) (129 buckets).  Decides whether (and with which tail capacity) the cell

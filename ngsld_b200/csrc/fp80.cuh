@@ -243,7 +243,84 @@ X87_HD int32_t mul_round(uint64_t a, uint64_t b, uint64_t &out) {
   return (int32_t)(top + carry);
 }
 
+// Straight-line form of the same step (what the r2_ExpG inner loop runs): identical results to mac_ratio_ref below
+// (the first, case-by-case version, kept as the cross-check in tests/native/fp80_check.cpp), organised so that a GPU
+// executes it as one predicated block instead of a dozen divergent branches:
+//   * both operands are aligned in one 128-bit window under the larger one; an exponent distance above 66 is clamped to
+//     66 (the small operand then only leaves a sticky trace below the guard bit, which can never change the result);
+//   * a subtraction is the addition of the two's complement (the bits that fell off the window turn the +1 into +0);
+//   * one normalisation (one place to the right after a carry, or clz places to the left after a cancellation) and one
+//     rounding serve both cases.
 X87_HD void mac_ratio(ext &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
+  if (asig == 0 || bsig == 0) return;  // a zero term leaves the (never -0) accumulator unchanged
+  uint64_t psig, t;
+  int32_t e = (int32_t)((ase & 0x7fffu) + (bse & 0x7fffu)) - 2 * 16383;
+  e += mul_round(asig, bsig, psig);     // P = fl80(a * b)
+  e += mul_round(psig, rsig, t) - 1;    // T = fl80(P * r), r.exp = -1
+  const uint32_t tneg = ((ase ^ bse) >> 15) & 1u;
+  if (acc.sig == 0) {  // first term
+    acc.sig = t;
+    acc.exp = e;
+    acc.neg = tneg;
+    return;
+  }
+  const int32_t dd = acc.exp - e;
+  const bool swap = dd < 0 || (dd == 0 && t > acc.sig);
+  const uint64_t big = swap ? t : acc.sig, small = swap ? acc.sig : t;
+  const uint32_t nbig = swap ? tneg : acc.neg;
+  const bool sub = (acc.neg ^ tneg) != 0;
+  int32_t er = swap ? e : acc.exp;
+  uint32_t d = (uint32_t)(dd < 0 ? -dd : dd);
+  d = d > 66u ? 66u : d;
+  // small under big (= big:0) as shi:slo, bits below the window in `sticky`
+  const uint32_t k = d & 63u;
+  const uint64_t xh = small >> k, xl = k ? small << (64u - k) : 0ull;
+  const bool far = d >= 64u;
+  const uint64_t shi = far ? 0ull : xh, slo = far ? xh : xl;
+  uint32_t sticky = far ? (uint32_t)(xl != 0) : 0u;
+  // big:0 + shi:slo, or big:0 - shi:slo - (sticky ? something below the window : 0) as a two's-complement addition
+  const uint64_t m = sub ? ~0ull : 0ull;
+  const uint64_t cin = sub ? (uint64_t)(1u - sticky) : 0ull;
+  uint64_t lo = (slo ^ m) + cin;
+  const uint64_t c1 = (uint64_t)(lo < cin);
+  const uint64_t y = (shi ^ m) + c1;          // cannot wrap: shi ^ m == ~0 needs shi == 0, slo == 0 -> handled by c1 <= 1 below
+  const uint64_t cy = (uint64_t)(y < c1);
+  uint64_t hi = big + y;
+  const bool carry_out = (hi < big) || cy;  // addition: a carry out of bit 127; subtraction: always set (no borrow)
+  if (sub && (hi | lo) == 0) {  // exact cancellation -> +0
+    acc.sig = 0;
+    acc.exp = 0;
+    acc.neg = 0;
+    return;
+  }
+  if (!sub && carry_out) {  // one place to the right
+    sticky |= (uint32_t)(lo & 1);
+    lo = (lo >> 1) | (hi << 63);
+    hi = (hi >> 1) | 0x8000000000000000ull;
+    er += 1;
+  }
+  if (sub) {  // up to 127 places to the left
+    if (hi == 0) {
+      hi = lo;
+      lo = 0;
+      er -= 64;
+    }
+    const int sh = clz64(hi);
+    if (sh) {
+      hi = (hi << sh) | (lo >> (64 - sh));
+      lo <<= sh;
+      er -= sh;
+    }
+  }
+  const uint64_t inc = (lo >> 63) & (uint64_t)((((lo << 1) != 0) | sticky) | (hi & 1));
+  hi += inc;
+  const uint32_t carry = hi == 0;
+  acc.sig = hi | ((uint64_t)carry << 63);
+  acc.exp = er + (int32_t)carry;
+  acc.neg = nbig;
+}
+
+X87_HD void mac_ratio_ref(ext &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
   if (asig == 0 || bsig == 0) return;  // a zero term leaves the (never -0) accumulator unchanged
   uint64_t psig, tsig;
   int32_t e = (int32_t)(ase & 0x7fff) + (int32_t)(bse & 0x7fff) - 2 * 16383;

@@ -200,4 +200,33 @@ void site_seeds(uint64_t seed, uint64_t n_sites, uint64_t *out) {
   }
 }
 
+void taus_jump_tables(uint32_t *jump) {
+  // one step of each component as a function of its own 32-bit state (GSL rng/taus.c)
+  auto step = [](int c, uint32_t x) -> uint32_t {
+    if (c == 0) return ((x & 4294967294u) << 12) ^ (((x << 13) ^ x) >> 19);
+    if (c == 1) return ((x & 4294967288u) << 4) ^ (((x << 2) ^ x) >> 25);
+    return ((x & 4294967280u) << 17) ^ (((x << 3) ^ x) >> 11);
+  };
+  auto apply = [](const uint32_t *cols, uint32_t x) -> uint32_t {
+    uint32_t y = 0;
+    for (int b = 0; b < 32; b++)
+      if ((x >> b) & 1u) y ^= cols[b];
+    return y;
+  };
+  for (int c = 0; c < 3; c++) {
+    uint32_t m[32], sq[32];
+    for (int b = 0; b < 32; b++) m[b] = step(c, 1u << b);  // the one-step matrix
+    int steps = 1;
+    for (int j = 0; j < TAUS_JUMP_LEVELS; j++) {
+      while (steps < TAUS_SEGMENT || j > 0) {  // square up to 512 steps for level 0, then once per level
+        for (int b = 0; b < 32; b++) sq[b] = apply(m, m[b]);
+        for (int b = 0; b < 32; b++) m[b] = sq[b];
+        steps *= 2;
+        if (j > 0) break;
+      }
+      for (int b = 0; b < 32; b++) jump[((size_t)j * 3 + c) * 32 + b] = m[b];
+    }
+  }
+}
+
 }  // namespace hostprep

@@ -31,4 +31,11 @@ struct TausStream {
   double uniform() { return get() / 4294967296.0; }
 };
 
+// Jump-ahead tables of the generator: each of its three components is a linear map over GF(2), so the state after
+// 512 * 2^j draws is a 32 x 32 bit-matrix product.  jump[j][c][b] = column b (image of bit b) of component c's matrix
+// for 512 * 2^j steps, j < TAUS_JUMP_LEVELS.  Lets a kernel start anywhere in a site's stream (aux::taus_sample_kernel).
+constexpr int TAUS_JUMP_LEVELS = 32;
+constexpr int TAUS_SEGMENT = 512;
+void taus_jump_tables(uint32_t *jump /* [TAUS_JUMP_LEVELS][3][32] */);
+
 }  // namespace hostprep

@@ -64,17 +64,20 @@ int main(int argc, char **argv) {
   }
   // the fused accumulate step of the r2_ExpG inner loop against native long double, including long random-walk
   // sums (cancellations, tiny terms under a large accumulator, zero terms)
-  for (int rep = 0; rep < 4000; rep++) {
+  const int mac_reps = argc > 2 ? atoi(argv[2]) : 4000;
+  for (int rep = 0; rep < mac_reps; rep++) {
     const int n_ind = 2 + (int)(g() % 700);
     volatile long double sum = 0.0L;
     x87::ext acc = x87::zero(0);
-    const int mode = rep % 6;
+    const int mode = rep % 8;
     for (int i = 1; i < n_ind; i++) {
       long double da = rnd_ld(mode == 0 ? 40 : 2), db = rnd_ld(mode == 1 ? 70 : 2);
       if (mode == 2 && i % 3 == 0) da = 0.0L;
       if (mode == 3 && i % 2 == 0) { da = 1.0L; db = -(long double)sum / ((long double)(i / (i + 1.0))); }  // near-exact cancellation
       if (mode == 4) { da = ldexpl(da, -(int)(g() % 140)); }
       if (mode == 5 && i == n_ind / 2) { da = 0x1p+60L; }
+      if (mode == 6) { da = ldexpl(da, (int)(g() % 140) - 70); if (i % 4 == 1) db = -db; }                 // wide exponent scatter, both signs
+      if (mode == 7 && i > 1) { da = 1.0L; db = -(long double)sum * (1.0L + ldexpl(1.0L, -(int)(g() % 66))) / ((long double)(i / (i + 1.0))); }  // cancellations that leave 1..66 low bits
       const long double ratio = i / (i + 1.0);
       sum += da * db * ratio;
       const x87::ext ea = from_ld(da), eb = from_ld(db);
@@ -82,7 +85,13 @@ int main(int argc, char **argv) {
       long double tda = da, tdb = db;
       memcpy(&as, &tda, 8); memcpy(&ae, (char *)&tda + 8, 2);
       memcpy(&bs, &tdb, 8); memcpy(&be, (char *)&tdb + 8, 2);
+      x87::ext acc_ref = acc;  // the case-by-case version of the same step must agree too
+      x87::mac_ratio_ref(acc_ref, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
       x87::mac_ratio(acc, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
+      if (acc_ref.sig != acc.sig || acc_ref.exp != acc.exp || acc_ref.neg != acc.neg) {
+        if (bad++ < 5) printf("mac_ratio != mac_ratio_ref rep %d mode %d i %d\n", rep, mode, i);
+        break;
+      }
       if (!same(acc, sum)) {
         if (bad++ < 5) printf("mac_ratio mismatch rep %d mode %d i %d: %La * %La\n", rep, mode, i, da, db);
         break;
