@@ -553,7 +553,7 @@ int main(int argc, char **argv) {
   off_t cursor = shards ? 0 : hl;
   struct PerGpu {
     uint64_t pairs = 0, passes = 0, launches = 0, slabs = 0, cells = 0, cell_pairs = 0, resid = 0;
-    double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0, s_scan = 0, s_wait = 0;
+    double ms_device = 0, ms_em = 0, ms_pearson = 0, ms_format = 0, ms_plan = 0, s_scan = 0, s_wait = 0;
   };
   std::vector<PerGpu> acc(n_gpu);
   struct PerWriter {
@@ -644,7 +644,7 @@ int main(int argc, char **argv) {
           acc[g].s_scan += wall_s() - ts0;
           acc[g].pairs += st.n_pairs; acc[g].passes += st.sum_em_passes; acc[g].launches += st.n_launches; acc[g].slabs++;
           acc[g].ms_device += st.ms_device_total; acc[g].ms_em += st.ms_em; acc[g].ms_pearson += st.ms_pearson;
-          acc[g].ms_format += st.ms_format; acc[g].cells += st.sum_cells; acc[g].cell_pairs += st.n_cell_pairs;
+          acc[g].ms_format += st.ms_format; acc[g].ms_plan += st.ms_plan; acc[g].cells += st.sum_cells; acc[g].cell_pairs += st.n_cell_pairs;
           acc[g].resid += st.n_resid_pairs;
           {
             std::lock_guard<std::mutex> lk(mu);
@@ -691,8 +691,8 @@ int main(int argc, char **argv) {
     uint64_t all_pairs = 0;
     for (int g = 0; g < n_gpu; g++) {
       all_pairs += acc[g].pairs;
-      fprintf(stderr, "[gpu %d] %lu slabs of %d: %lu pairs, %lu EM passes, %lu launches, scanning %.2f s (device %.1f ms: EM %.1f, r2_ExpG %.1f, format %.1f), waiting for a buffer %.2f s, %.0f pairs/s while scanning",
-              g, acc[g].slabs, n_slabs, acc[g].pairs, acc[g].passes, acc[g].launches, acc[g].s_scan, acc[g].ms_device, acc[g].ms_em,
+      fprintf(stderr, "[gpu %d] %lu slabs of %d: %lu pairs, %lu EM passes, %lu launches, scanning %.2f s (planning %.1f ms, device %.1f ms: EM %.1f, r2_ExpG %.1f, format %.1f), waiting for a buffer %.2f s, %.0f pairs/s while scanning",
+              g, acc[g].slabs, n_slabs, acc[g].pairs, acc[g].passes, acc[g].launches, acc[g].s_scan, acc[g].ms_plan, acc[g].ms_device, acc[g].ms_em,
               acc[g].ms_pearson, acc[g].ms_format, acc[g].s_wait, acc[g].s_scan > 0 ? acc[g].pairs / acc[g].s_scan : 0.0);
       if (acc[g].cell_pairs)
         fprintf(stderr, "; class-compressed EM: %.1f cells per pair, %lu pairs left to the dense kernel", (double)acc[g].cells / acc[g].cell_pairs, acc[g].resid);

@@ -183,10 +183,13 @@ void free_chunks(ngsld_ctx *c) {
   c->alloc_text = c->alloc_host = false;
 }
 
-int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, uint32_t slot) {
+// need_host: page-locked staging for binary rows; need_text: device text buffers; text_staging: page-locked staging for
+// the text as well (the sink variants; ngsld_scan_tsv_into copies straight into the caller's buffer instead)
+int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, uint32_t slot, bool text_staging = true) {
   if (rows < 1) rows = 1;
   // the text buffers are rows * slot bytes: a longer slot (extend_out, longer labels) needs new ones
-  if (c->alloc_rows >= rows && (!need_host || c->alloc_host) && (!need_text || (c->alloc_text && c->alloc_slot >= slot)))
+  if (c->alloc_rows >= rows && (!need_host || c->alloc_host) &&
+      (!need_text || (c->alloc_text && c->alloc_slot >= slot && (!text_staging || c->buf[0].h_text))))
     return NGSLD_OK;
   free_chunks(c);
   for (auto &b : c->buf) {
@@ -199,9 +202,8 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
       CUDA_TRY(c, cudaMalloc(&b.d_text, rows * (size_t)slot));
       CUDA_TRY(c, cudaMalloc(&b.d_text_out, rows * (size_t)slot));
       CUDA_TRY(c, cudaMalloc(&b.d_line_off, (rows + rows / 1024 + 8) * sizeof(unsigned long long)));
-      CUDA_TRY(c, cudaMallocHost(&b.h_text, rows * (size_t)slot));
+      if (text_staging) CUDA_TRY(c, cudaMallocHost(&b.h_text, rows * (size_t)slot));
       CUDA_TRY(c, cudaMallocHost(&b.h_text_len, 2 * sizeof(unsigned long long)));
-      CUDA_TRY(c, cudaMallocHost(&b.h_rows, rows * sizeof(ngsld_pair_row)));  // host-format fallback
     }
   }
   c->alloc_rows = rows;
@@ -876,13 +878,14 @@ int deliver_chunk(ngsld_ctx *c, ChunkBuf &b, const Delivery &d) {
       if (d.text_dst) return NGSLD_OK;
     } else {
       // some value was outside the device formatter's range: re-format this chunk with the host printf
-      CUDA_TRY(c, cudaMemcpyAsync(b.h_rows, b.d_rows, b.n_rows * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
+      std::vector<ngsld_pair_row> host_rows(b.n_rows);  // rare path: pageable is fine
+      CUDA_TRY(c, cudaMemcpyAsync(host_rows.data(), b.d_rows, b.n_rows * sizeof(ngsld_pair_row), cudaMemcpyDeviceToHost, c->s_copy));
       CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
       c->stats.d2h_bytes += b.n_rows * sizeof(ngsld_pair_row);
       std::string txt;
       char line[2048];
       for (uint64_t k = 0; k < b.n_rows; k++) {
-        const ngsld_pair_row &r = b.h_rows[k];
+        const ngsld_pair_row &r = host_rows[k];
         const char *l1 = c->have_labels ? c->h_labels[r.s1].c_str() : "(null)";
         const char *l2 = c->have_labels ? c->h_labels[r.s2].c_str() : "(null)";
         const int m = fmt::format_row_host(r, l1, l2, c->h_maf[r.s1], c->h_maf[r.s2], d.extend_out, line, sizeof line);
@@ -957,7 +960,8 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
     fa.slot = slot;
   }
   uint64_t chunk = std::min<unsigned long long>(c->chunk_rows, pl.total);
-  if (d.mode == MODE_TEXT) chunk = std::min<uint64_t>(chunk, 1ull << 20);
+  // text through a sink is staged in page-locked chunk buffers of the context: keep those at 1 M rows
+  if (d.mode == MODE_TEXT && !d.text_dst) chunk = std::min<uint64_t>(chunk, 1ull << 20);
   const bool use_tiles = ch.tile && ch.v && !ch.w && !P.strict;
   std::vector<uint2> tiles;
   std::vector<size_t> block_off;
@@ -978,9 +982,10 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
       c->stats.h2d_bytes += tiles.size() * sizeof(uint2);
     }
   }
-  rc = ensure_chunks(c, chunk, d.mode == MODE_ROWS, d.mode == MODE_TEXT, slot);
+  rc = ensure_chunks(c, chunk, d.mode == MODE_ROWS && !d.rows_dst, d.mode == MODE_TEXT, slot, d.text_dst == nullptr);
   if (rc) return rc;
   CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->s_main));
+  c->stats.ms_plan = now_ms() - t_plan0;  // everything on the host before the first launch: plan, kernel choice, buffers
   CUDA_TRY(c, cudaEventRecord(c->ev_begin, c->s_main));
   unsigned long long r0 = 0;
   size_t ab0 = 0;

@@ -85,11 +85,11 @@ int main(int argc, char **argv) {
       long double tda = da, tdb = db;
       memcpy(&as, &tda, 8); memcpy(&ae, (char *)&tda + 8, 2);
       memcpy(&bs, &tdb, 8); memcpy(&be, (char *)&tdb + 8, 2);
-      x87::ext acc_ref = acc;  // the case-by-case version of the same step must agree too
-      x87::mac_ratio_ref(acc_ref, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
+      x87::ext acc_ref = acc;  // the straight-line version of the same step must agree too
+      x87::mac_ratio_flat(acc_ref, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
       x87::mac_ratio(acc, as, ae, bs, be, x87::ratio_sig((double)i / ((double)i + 1.0)));
       if (acc_ref.sig != acc.sig || acc_ref.exp != acc.exp || acc_ref.neg != acc.neg) {
-        if (bad++ < 5) printf("mac_ratio != mac_ratio_ref rep %d mode %d i %d\n", rep, mode, i);
+        if (bad++ < 5) printf("mac_ratio != mac_ratio_flat rep %d mode %d i %d\n", rep, mode, i);
         break;
       }
       if (!same(acc, sum)) {
