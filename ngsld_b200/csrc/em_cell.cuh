@@ -31,6 +31,14 @@
 #include "em_fast.cuh"
 #include "pearson.cuh"
 
+// compile-time experiment switches (A/B builds: make ALT=... in csrc/Makefile)
+#ifndef NGSLD_CELL_PRELOAD
+#define NGSLD_CELL_PRELOAD 1
+#endif
+#ifndef NGSLD_CELL_SMEM_BCAST
+#define NGSLD_CELL_SMEM_BCAST 1
+#endif
+
 namespace emcell {
 
 constexpr int WARPS_PER_CTA = 4;
@@ -70,9 +78,30 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
   const uint64_t miss1 = ign ? T.pal_miss[s1] : 0ull, miss2 = ign ? T.pal_miss[s2] : 0ull;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t n_cells = 0, used = 0;
+#if NGSLD_CELL_PRELOAD
+  // the class words of the first four blocks (512 individuals) are requested together, ahead of the counting loop: one
+  // trip to L2 instead of one per block
+  uint32_t pre1[4], pre2[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const uint32_t i0 = 128u * b + 4u * (uint32_t)lane;
+    pre1[b] = pre2[b] = 0;
+    if (i0 < T.n_ind) {
+      pre1[b] = *reinterpret_cast<const uint32_t *>(c1 + i0);
+      pre2[b] = *reinterpret_cast<const uint32_t *>(c2 + i0);
+    }
+  }
+#endif
   for (uint32_t blk = 0; blk < T.n_ind; blk += 128u) {
     const uint32_t i0 = blk + 4u * (uint32_t)lane;  // this lane's four individuals of the block
     uint32_t w1 = 0, w2 = 0;
+#if NGSLD_CELL_PRELOAD
+    if (blk < 512u) {  // (warp-uniform; the loop is not unrolled, so the four words are picked by comparison)
+      const uint32_t b = blk >> 7;
+      w1 = b == 0 ? pre1[0] : b == 1 ? pre1[1] : b == 2 ? pre1[2] : pre1[3];
+      w2 = b == 0 ? pre2[0] : b == 1 ? pre2[1] : b == 2 ? pre2[2] : pre2[3];
+    } else
+#endif
     if (i0 < T.n_ind) {
       w1 = *reinterpret_cast<const uint32_t *>(c1 + i0);
       w2 = *reinterpret_cast<const uint32_t *>(c2 + i0);
@@ -166,7 +195,7 @@ __device__ __forceinline__ double warp_sum4_own(double a0, double a1, double a2,
 template <int L, int R>
 __device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double *tail, uint32_t tcap, uint32_t n_tail_pad,
                                                double inv_x, int lane, double &f0, double &f1, double &f2, double &f3,
-                                               double &Aq, bool &conv) {
+                                               double &Aq, bool &conv, uint32_t fbuf) {
   double fq = (lane & 16) ? ((lane & 8) ? f3 : f2) : ((lane & 8) ? f1 : f0);
   uint32_t it = 0;
   for (;;) {
@@ -190,11 +219,22 @@ __device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double 
     const double nq = Aq * inv_x;
     const bool moved = fabs(nq - fq) >= NGSLD_EPS;  // false for a NaN difference
     fq = nq;
+#if NGSLD_CELL_SMEM_BCAST
+    // the four new frequencies go round through four doubles of the warp's shared memory (one store by the first lane of
+    // each quadrant, two 128-bit broadcast loads) instead of eight shuffles
+    if ((lane & 7) == 0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(fbuf + (uint32_t)(lane >> 3) * 8u), "d"(nq) : "memory");
+    __syncwarp();
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(f0), "=d"(f1) : "r"(fbuf) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(f2), "=d"(f3) : "r"(fbuf + 16u) : "memory");
+    __syncwarp();  // every lane has read the four values before the next pass stores again
+    conv = !__any_sync(0xffffffffu, moved);
+#else
     f0 = __shfl_sync(0xffffffffu, nq, 0);
     f1 = __shfl_sync(0xffffffffu, nq, 8);
     f2 = __shfl_sync(0xffffffffu, nq, 16);
     f3 = __shfl_sync(0xffffffffu, nq, 24);
     conv = !__any_sync(0xffffffffu, moved);
+#endif
     if (conv || it == NGSLD_ITER_MAX - 1) break;
     it++;
   }
@@ -206,7 +246,9 @@ __device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double 
 template <int R, bool FUSE, int MINB>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T, PairChunk C, CellArgs A, DevCounters *ctr) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ __align__(16) double fbuf_all[WARPS_PER_CTA][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t fbuf = (uint32_t)__cvta_generic_to_shared(fbuf_all[warp]);  // 32-bit shared address: one register
   const uint32_t cap = 32u * R + A.tcap;
   unsigned char *mine = dyn_smem + (size_t)warp * warp_smem_bytes(R, A.tcap, A.kstride);
   uint16_t *bins = reinterpret_cast<uint16_t *>(mine);
@@ -283,13 +325,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       uint32_t it = 0;
       bool conv = false;
       switch (n_lev) {  // warp-uniform; empty register levels are skipped as a whole
-        case 0: it = em_iterate<0, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        case 1: it = em_iterate<1, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        case 2: it = em_iterate<(R < 2 ? R : 2), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        case 3: it = em_iterate<(R < 3 ? R : 3), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        case 4: it = em_iterate<(R < 4 ? R : 4), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        case 5: it = em_iterate<(R < 5 ? R : 5), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
-        default: it = em_iterate<R, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv); break;
+        case 0: it = em_iterate<0, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 1: it = em_iterate<1, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 2: it = em_iterate<(R < 2 ? R : 2), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 3: it = em_iterate<(R < 3 ? R : 3), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 4: it = em_iterate<(R < 4 ? R : 4), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 5: it = em_iterate<(R < 5 ? R : 5), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        default: it = em_iterate<R, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
       }
       const double A0 = __shfl_sync(0xffffffffu, Aq, 0), A1 = __shfl_sync(0xffffffffu, Aq, 8),
                    A2 = __shfl_sync(0xffffffffu, Aq, 16), A3 = __shfl_sync(0xffffffffu, Aq, 24);
