@@ -192,6 +192,9 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
       (!need_text || (c->alloc_text && c->alloc_slot >= slot && (!text_staging || c->buf[0].h_text))))
     return NGSLD_OK;
   free_chunks(c);
+  // successive scans of one job (the slabs of the CLI) differ a little in size: leave headroom, or every slab that is a
+  // few rows larger than all before would pay for a reallocation
+  if (rows > (1u << 20)) rows = std::min<uint64_t>(rows + rows / 8, std::max<uint64_t>(rows, c->chunk_rows));
   for (auto &b : c->buf) {
     CUDA_TRY(c, cudaMalloc(&b.d_s1, rows * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&b.d_s2, rows * sizeof(uint32_t)));
@@ -583,7 +586,9 @@ int launch_warp(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
 }
 
 // The class-compressed kernel on a chunk, then the dense kernel on whatever it left over (same stream).
-int launch_cell(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss, uint32_t *d_resid) {
+// row_len: pairs per first site in this chunk (0 = unknown / irregular): shapes the work order, see CellArgs::swz_len
+int launch_cell(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const PairChunk &C, int ignore_miss, uint32_t *d_resid,
+                uint64_t row_len = 0) {
   SiteTable Tt = T;
   PairChunk Cc = C;
   DevCounters *ctr = c->d_ctr;
@@ -593,6 +598,12 @@ int launch_cell(ngsld_ctx *c, const EmChoice &ch, const SiteTable &T, const Pair
   A.ignore_miss = ignore_miss;
   A.fuse_pearson = ch.cell_fuse ? 1 : 0;
   A.kstride = c->cell_kstride;
+  A.swz_len = A.swz_rows = 0;
+  static const bool no_swizzle = getenv("NGSLD_CELL_LINEAR") && atoi(getenv("NGSLD_CELL_LINEAR"));
+  if (!no_swizzle && row_len >= 64 && row_len < C.n_pairs && row_len < (1ull << 31)) {
+    A.swz_len = (uint32_t)row_len;
+    A.swz_rows = (uint32_t)((C.n_pairs + row_len - 1) / row_len);
+  }
   void *args[] = {&Tt, &Cc, &A, &ctr};
   const unsigned long long want = (C.n_pairs + 32ull * emcell::WARPS_PER_CTA - 1) / (32ull * emcell::WARPS_PER_CTA);
   const unsigned blocks = (unsigned)std::min<unsigned long long>(want, ch.blocks_cell);
@@ -762,7 +773,11 @@ int launch_chunk(ngsld_ctx *c, const Plan &pl, const ngsld_scan_params &P, const
     const unsigned sb = (unsigned)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)c->sm_count * 64);
     aux::em_strict_kernel<<<sb, 128, 0, c->s_main>>>(T, C, P.ignore_miss_data, c->d_ctr);
   } else if (use_cell) {
-    int rcc = launch_cell(c, ch, T, C, P.ignore_miss_data, b.d_resid);
+    // pairs per first site around here: the window of the chunk's first site (windows shrink or shift by about one pair
+    // per site, which the work order tolerates); sampled scans keep the listed order
+    uint64_t row_len = 0;
+    if (!pl.sampled && pl.cw_end[ca] > ca + 1) row_len = pl.cw_end[ca] - ca - 1;
+    int rcc = launch_cell(c, ch, T, C, P.ignore_miss_data, b.d_resid, row_len);
     if (rcc) return rcc;
   } else if (ch.w) {
     int rcw = launch_warp(c, ch, T, C, P.ignore_miss_data);
@@ -937,12 +952,15 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
     b.pending = false;
   }
   const double t_plan0 = now_ms();
+  static const bool dbg = getenv("NGSLD_DEBUG_PLAN") && atoi(getenv("NGSLD_DEBUG_PLAN"));
   Plan pl;
   int rc = make_plan(plan_input(c), s1_lo, s1_hi, P, pl);
   if (rc) return rc;
+  const double t_plan1 = now_ms();
   rc = upload_plan(c, pl, P);
   if (rc) return rc;
   c->stats.ms_plan = now_ms() - t_plan0;
+  const double t_plan2 = now_ms();
   if (pl.total == 0) return NGSLD_OK;
   if (d.rows_dst && pl.total > d.text_cap) return fail(c, NGSLD_E_INVALID, "output buffer too small for this scan");
   EmChoice ch;
@@ -986,6 +1004,9 @@ int run_scan(ngsld_ctx *c, uint64_t s1_lo, uint64_t s1_hi, const ngsld_scan_para
   if (rc) return rc;
   CUDA_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->s_main));
   c->stats.ms_plan = now_ms() - t_plan0;  // everything on the host before the first launch: plan, kernel choice, buffers
+  if (dbg)
+    fprintf(stderr, "[plan] rows %llu: make_plan %.2f ms, upload_plan %.2f ms, kernel choice + buffers %.2f ms\n", pl.total,
+            t_plan1 - t_plan0, t_plan2 - t_plan1, now_ms() - t_plan2);
   CUDA_TRY(c, cudaEventRecord(c->ev_begin, c->s_main));
   unsigned long long r0 = 0;
   size_t ab0 = 0;
@@ -1240,9 +1261,10 @@ int finish_sites(ngsld_ctx *c, const double *host_expg) {
       }
       c->cell_p995 = 32u * (std::min<uint32_t>(b, 128) + 1);
       c->cell_possible = true;
-      // pays when a pair has clearly fewer cells than individuals and (almost) every site could be coded; below 160
-      // individuals the sub-warp group kernels are the better fit
-      c->cell_ok = n_ind >= 160 && c->cell_uncoded_frac <= 0.05 && c->cell_mean <= 0.7 * (double)n_ind;
+      // pays when a pair has clearly fewer cells than individuals and (almost) every site could be coded (measured at 100
+      // individuals, 65 cells per pair: 96.7 M pairs/s against 80.3 M for the sub-warp group kernels); small samples stay
+      // with the group kernels
+      c->cell_ok = n_ind >= 64 && c->cell_uncoded_frac <= 0.05 && c->cell_mean <= 0.7 * (double)n_ind;
     }
   }
   // per-site x87 terms of the expected-genotype correlation

@@ -32,11 +32,13 @@
 #include "pearson.cuh"
 
 // compile-time experiment switches (A/B builds: make ALT=... in csrc/Makefile)
+// Both measured SLOWER than the plain forms at the 128-register budget of the default variant (53.5 vs 58.2 M pairs/s with
+// both on, round 2): they stay off.
 #ifndef NGSLD_CELL_PRELOAD
-#define NGSLD_CELL_PRELOAD 1
+#define NGSLD_CELL_PRELOAD 0
 #endif
 #ifndef NGSLD_CELL_SMEM_BCAST
-#define NGSLD_CELL_SMEM_BCAST 1
+#define NGSLD_CELL_SMEM_BCAST 0
 #endif
 
 namespace emcell {
@@ -54,6 +56,13 @@ struct CellArgs {
   int ignore_miss;    // --ignore_miss_data: individuals whose class is flat at either site are left out
   int fuse_pearson;   // compute r2_ExpG in this kernel
   uint32_t kstride;   // row length of the joint-class table: the largest palette of the data set, rounded up to 8
+  // Order in which the batches of 32 pairs are worked through.  The chunk's pairs are listed first site by first site;
+  // taken in that order, the warps resident at one time share a first site and sweep the whole second-site axis, so every
+  // second site's data (x87 terms, class row, palette) comes from DRAM once per first site.  With swz_len = L > 0 the
+  // list is read as a matrix of rows of L pairs (about one first site per row) and walked 32 columns at a time, all rows
+  // of a column block before the next block: the second sites of a block are then fetched once and serve every first
+  // site of the chunk out of L2.  Only the order of the work changes, not where a pair's row is written.
+  uint32_t swz_len, swz_rows;
 };
 
 // shared memory of one warp: joint-class counters | cell keys | tail cells (7 doubles each, structure of arrays)
@@ -258,13 +267,25 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
   const bool ign = A.ignore_miss != 0;
   unsigned long long my_passes = 0, my_cell_passes = 0, my_cells = 0, my_pairs = 0, my_resid = 0;
 
+  const unsigned long long n_batches =
+      A.swz_len ? (unsigned long long)A.swz_rows * ((A.swz_len + 31u) / 32u) : (C.n_pairs + 31ull) / 32ull;
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&ctr->next_pair, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= C.n_pairs) break;
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(&ctr->next_pair, 1ull);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= n_batches) break;
+    unsigned long long base = b * 32ull;
+    uint32_t width = 32;  // pairs of this batch
+    if (A.swz_len) {
+      const unsigned long long cb = b / A.swz_rows, r = b - cb * A.swz_rows;  // column block, matrix row
+      const uint32_t c0 = (uint32_t)cb * 32u;
+      base = r * A.swz_len + c0;
+      width = A.swz_len - c0 < 32u ? A.swz_len - c0 : 32u;
+    }
+    if (base >= C.n_pairs) continue;
+    if (C.n_pairs - base < width) width = (uint32_t)(C.n_pairs - base);
     const unsigned long long me = base + lane;
-    const bool have = me < C.n_pairs;
+    const bool have = (uint32_t)lane < width;
     uint32_t my_s1 = 0, my_s2 = 0;
     if (have) {
       my_s1 = C.s1[me];
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
     // ---- r2_ExpG of the batch, one pair per lane ----
     if (FUSE && have) C.rows[me].r2_expg = pearson::pair_r2(T, my_s1, my_s2);
     __syncwarp();
-    const int nb = C.n_pairs - base < 32ull ? (int)(C.n_pairs - base) : 32;
+    const int nb = (int)width;
 
     // ---- the batch's EMs, the whole warp on one pair at a time ----
     for (int j = 0; j < nb; j++) {
