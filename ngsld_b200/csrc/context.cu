@@ -627,7 +627,7 @@ int choose_cell(ngsld_ctx *c, EmChoice &ch) {
   const emcell::CellVariant *v = nullptr;
   for (int k = 0; k < emcell::cell_variants_count; k++)
     if (emcell::cell_variants[k].r == r && (!v || emcell::cell_variants[k].minb == minb)) v = &emcell::cell_variants[k];
-  if (!v) v = &emcell::cell_variants[emcell::cell_variants_count - 2];
+  if (!v) v = &emcell::cell_variants[emcell::cell_variants_count - 1];
   r = v->r;
   uint32_t tcap = c->cell_p995 > 32u * r ? ((c->cell_p995 - 32u * r + 63u) & ~63u) : 0u;
   tcap = std::max<uint32_t>(tcap, 64);  // room for the odd pair beyond the sampled percentile

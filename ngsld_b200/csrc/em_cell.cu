@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(CTA_THREADS) cell_stats_kernel(SiteTable T, ui
 }
 
 #define V(r, b) {r, b, (const void *)em_cell_kernel<r, false, b>, (const void *)em_cell_kernel<r, true, b>}
-extern const CellVariant cell_variants[] = {V(2, 4), V(4, 3), V(4, 4), V(6, 3), V(6, 4)};
+extern const CellVariant cell_variants[] = {V(2, 4), V(2, 5), V(4, 3), V(4, 4), V(4, 5), V(6, 3), V(6, 4)};
 #undef V
-extern const int cell_variants_count = 5;
+extern const int cell_variants_count = 7;
 
 }  // namespace emcell
