@@ -110,33 +110,41 @@ __global__ void __launch_bounds__(128) pearson_kernel(SiteTable T, PairChunk C, 
 //     mean = x[0];  for i >= 1:  delta_i = x[i] - mean;  sum_sq += delta_i * delta_i * ratio_i;  mean += delta_i / (i + 1.0)
 // all in x87 extended precision (ratio_i = i / (i + 1.0) is a double division widened).  Stores the 80-bit memory image
 // of every delta_i and q = sqrt((double)sum_sq).  One thread per site; the recurrence is sequential in i.
-__global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad,
+__global__ void __launch_bounds__(128) site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_blk,
                                                          uint64_t *dx_sig, uint16_t *dx_se, double *q, uint64_t *ratio) {
   // the ratio table shared by every pair: significand of (long double)(i / (i + 1.0))
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_pad; i += gridDim.x * blockDim.x)  // n_pad + 1 entries
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * n_blk; i += gridDim.x * blockDim.x)
     ratio[i] = i ? x87::ratio_sig(__ddiv_rn((double)i, __dadd_rn((double)i, 1.0))) : 0ull;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
     const double *x = expg + (size_t)s * n_ind;
-    uint64_t *sig = dx_sig + s;  // individual-major: element i of site s lives at [i * n_sites + s]
-    uint16_t *se = dx_se + s;
+    // element i of site s lives at [(i / 4) * n_sites + s][i % 4]: four individuals are collected and stored together
     x87::ext mean = x87::from_double(x[0]);
     x87::ext ssq = x87::zero(0);
-    sig[0] = 0;
-    se[0] = 0;
-    for (uint32_t i = 1; i < n_ind; i++) {
-      const double ip1 = __dadd_rn((double)i, 1.0);
-      const x87::ext ratio = x87::from_double(__ddiv_rn((double)i, ip1));
-      x87::ext neg_mean = mean;
-      neg_mean.neg ^= 1u;
-      const x87::ext delta = x87::add(x87::from_double(x[i]), neg_mean);
-      ssq = x87::add(ssq, x87::mul(x87::mul(delta, delta), ratio));
-      mean = x87::add(mean, x87::div(delta, x87::from_double(ip1)));
-      sig[(size_t)i * n_sites] = delta.sig;
-      se[(size_t)i * n_sites] = (uint16_t)((delta.neg << 15) | (delta.sig ? (uint32_t)(delta.exp + 16383) : 0u));
-    }
-    for (uint32_t i = n_ind; i < n_pad; i++) {
-      sig[(size_t)i * n_sites] = 0;
-      se[(size_t)i * n_sites] = 0;
+    for (uint32_t blk = 0; blk < n_blk; blk++) {
+      uint64_t sig4[4];
+      uint16_t se4[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t i = 4u * blk + j;
+        sig4[j] = 0;
+        se4[j] = 0;
+        if (i == 0 || i >= n_ind) continue;
+        const double ip1 = __dadd_rn((double)i, 1.0);
+        const x87::ext ratio = x87::from_double(__ddiv_rn((double)i, ip1));
+        x87::ext neg_mean = mean;
+        neg_mean.neg ^= 1u;
+        const x87::ext delta = x87::add(x87::from_double(x[i]), neg_mean);
+        ssq = x87::add(ssq, x87::mul(x87::mul(delta, delta), ratio));
+        mean = x87::add(mean, x87::div(delta, x87::from_double(ip1)));
+        sig4[j] = delta.sig;
+        se4[j] = x87::se14_pack(delta.neg, delta.exp, delta.sig);
+      }
+      const size_t at = (size_t)blk * n_sites + s;
+      ulonglong2 *ps = reinterpret_cast<ulonglong2 *>(dx_sig) + 2 * at;
+      ps[0] = make_ulonglong2(sig4[0], sig4[1]);
+      ps[1] = make_ulonglong2(sig4[2], sig4[3]);
+      reinterpret_cast<uint2 *>(dx_se)[at] =
+          make_uint2((uint32_t)se4[0] | ((uint32_t)se4[1] << 16), (uint32_t)se4[2] | ((uint32_t)se4[3] << 16));
     }
     q[s] = __dsqrt_rn(x87::to_double(ssq));
   }

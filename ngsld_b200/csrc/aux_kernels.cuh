@@ -5,7 +5,7 @@
 namespace aux {
 __global__ void em_strict_kernel(SiteTable T, PairChunk C, int ignore_miss, DevCounters *ctr);
 __global__ void pearson_kernel(SiteTable T, PairChunk C, DevCounters *ctr);
-__global__ void site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_pad, uint64_t *dx_sig,
+__global__ void site_terms_kernel(const double *expg, uint32_t n_sites, uint32_t n_ind, uint32_t n_blk, uint64_t *dx_sig,
                                   uint16_t *dx_se, double *q, uint64_t *ratio);
 __global__ void expand_window_kernel(const unsigned long long *row_off, const uint32_t *cs, uint32_t n_compact,
                                      unsigned long long row_lo, unsigned long long n, uint32_t *s1, uint32_t *s2);

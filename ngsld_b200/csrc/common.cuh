@@ -11,11 +11,12 @@
 struct SiteTable {
   const double *gl;        // [n_sites][n_pad][3] normal-space genotype likelihoods, rows 16-byte aligned
   const double *maf;       // [n_sites]
-  const uint64_t *dx_sig;  // [n_pad][n_sites] (individual-major) x87 significand of the Pearson deviation x[i]-mean_(i-1):
-                           // the 32 pairs of a warp share s1 and have consecutive s2, so their loads coalesce
-  const uint16_t *dx_se;   // [n_pad][n_sites] sign|biased exponent of the same
+  const uint64_t *dx_sig;  // [n_blk][n_sites][4] x87 significand of the Pearson deviation x[i]-mean_(i-1) of individual
+                           // i = 4 blk + j (zero for i = 0 and behind the last individual): the 32 pairs of a warp share
+                           // s1 and have consecutive s2, so a block row is read as one coalesced 1 KB request
+  const uint16_t *dx_se;   // [n_blk][n_sites][4] sign and exponent of the same, packed for mac3 (fp80.cuh, "se14")
   const double *q;         // [n_sites] sqrt((double)sum_xsq)
-  const uint64_t *ratio;   // [n_pad] x87 significand of (long double)(i / (i + 1.0)) (exponent -1); entry 0 unused
+  const uint64_t *ratio;   // [4 n_blk] x87 significand of (long double)(i / (i + 1.0)) (exponent -1); entry 0 unused
   const double *cum;       // [n_sites] exact prefix sum of finite pos_dist (NULL: no positions)
   const uint32_t *seg;     // [n_sites] chromosome segment id (increments at each +inf pos_dist)
   // site palettes (em_cell.cuh): the DISTINCT genotype-likelihood triples of a site and, per individual, which one it has
@@ -24,6 +25,7 @@ struct SiteTable {
   const uint8_t *pal_k;    // [n_sites] number of classes; 0 = more than NGSLD_KMAX distinct triples (site not coded)
   const uint64_t *pal_miss;  // [n_sites] bit c set: class c is "missing data" (flat triple, gl_missing)
   uint32_t n_sites, n_ind, n_pad, n_cpad;
+  uint32_t n_blk;          // (n_ind + 3) / 4: blocks of four individuals in dx_sig / dx_se
 };
 
 #define NGSLD_KMAX 64  // classes per site palette (joint classes of a pair index a 64 x 64 table of 16-bit counts)

@@ -239,10 +239,14 @@ int alloc_site_buffers(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind, bool with
     CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
     // (one spare row / entry behind the tables: the r2_ExpG loop requests the operands of individual i + 1 unconditionally)
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * (n_pad + 1) * sizeof(uint64_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * (n_pad + 1) * sizeof(uint16_t)));
+    const uint64_t n_blk = (n_ind + 3) / 4;  // x87 terms: blocks of four individuals
+    // (one spare block row behind the last: pearson::pair_r2 requests "the next block" without a guard)
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * (n_blk + 1) * 4 * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_dx_se, n_sites * (n_blk + 1) * 4 * sizeof(uint16_t)));
+    CUDA_TRY(c, cudaMemset(c->d_dx_sig + n_sites * n_blk * 4, 0, n_sites * 4 * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMemset(c->d_dx_se + n_sites * n_blk * 4, 0, n_sites * 4 * sizeof(uint16_t)));
     CUDA_TRY(c, cudaMalloc(&c->d_seg, n_sites * sizeof(uint32_t)));
-    CUDA_TRY(c, cudaMalloc(&c->d_ratio, (n_pad + 1) * sizeof(uint64_t)));
+    CUDA_TRY(c, cudaMalloc(&c->d_ratio, n_blk * 4 * sizeof(uint64_t)));
     if (n_ind < 65536) {  // joint-class counters are 16 bits wide
       CUDA_TRY(c, cudaMalloc(&c->d_cls, n_sites * n_cpad));
       CUDA_TRY(c, cudaMalloc(&c->d_pal, n_sites * (size_t)NGSLD_KMAX * 3 * sizeof(double)));
@@ -273,6 +277,7 @@ SiteTable site_table(const ngsld_ctx *c) {
   T.n_sites = (uint32_t)c->n_sites;
   T.n_ind = (uint32_t)c->n_ind;
   T.n_pad = (uint32_t)c->n_pad;
+  T.n_blk = (uint32_t)((c->n_ind + 3) / 4);
   return T;
 }
 
@@ -1225,6 +1230,7 @@ int begin_sites(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind) {
 // palettes, decide about the class-compressed EM, and compute the per-site x87 terms of r2_ExpG.
 int finish_sites(ngsld_ctx *c, const double *host_expg) {
   const uint64_t n_sites = c->n_sites, n_ind = c->n_ind, n_pad = c->n_pad, n_cpad = c->n_cpad;
+  const uint64_t n_blk = (n_ind + 3) / 4;
   // site palettes for the class-compressed EM, and a sample of pairs to see whether it pays on this data
   c->cell_ok = c->cell_possible = false;
   c->cell_mean = c->cell_uncoded_frac = 0;
@@ -1276,13 +1282,14 @@ int finish_sites(ngsld_ctx *c, const double *host_expg) {
     std::vector<double> q(n_sites);
     const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
     hostprep::pearson_site_terms(host_expg, n_sites, n_ind, n_pad, nt, sig.data(), se.data(), q.data());
-    {  // the device table is individual-major
-      std::vector<uint64_t> sig_t(sig.size());
-      std::vector<uint16_t> se_t(se.size());
+    {  // the device table holds blocks of four individuals, site by site inside a block, in mac3's packed exponent form
+      std::vector<uint64_t> sig_t(n_sites * n_blk * 4, 0);
+      std::vector<uint16_t> se_t(n_sites * n_blk * 4, 0);
       for (uint64_t s = 0; s < n_sites; s++)
-        for (uint64_t i = 0; i < n_pad; i++) {
-          sig_t[i * n_sites + s] = sig[s * n_pad + i];
-          se_t[i * n_sites + s] = se[s * n_pad + i];
+        for (uint64_t i = 1; i < n_ind; i++) {
+          const uint64_t at = ((i >> 2) * n_sites + s) * 4 + (i & 3);
+          sig_t[at] = sig[s * n_pad + i];
+          se_t[at] = sig_t[at] ? x87::se14_from_x87(se[s * n_pad + i]) : (uint16_t)0;
         }
       sig.swap(sig_t);
       se.swap(se_t);
@@ -1290,11 +1297,11 @@ int finish_sites(ngsld_ctx *c, const double *host_expg) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_sig, sig.data(), sig.size() * 8, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_dx_se, se.data(), se.size() * 2, cudaMemcpyHostToDevice, c->s_main));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_q, q.data(), q.size() * 8, cudaMemcpyHostToDevice, c->s_main));
-    aux::site_terms_kernel<<<8, 128, 0, c->s_main>>>(nullptr, 0, 0, (uint32_t)n_pad, nullptr, nullptr, nullptr, c->d_ratio);
+    aux::site_terms_kernel<<<8, 128, 0, c->s_main>>>(nullptr, 0, 0, (uint32_t)n_blk, nullptr, nullptr, nullptr, c->d_ratio);
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
   } else {
     const unsigned blocks = (unsigned)std::min<uint64_t>((n_sites + 127) / 128, (uint64_t)c->sm_count * 16);
-    aux::site_terms_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_expg, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_pad,
+    aux::site_terms_kernel<<<blocks, 128, 0, c->s_main>>>(c->d_expg, (uint32_t)n_sites, (uint32_t)n_ind, (uint32_t)n_blk,
                                                           c->d_dx_sig, c->d_dx_se, c->d_q, c->d_ratio);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->s_main));
@@ -1657,10 +1664,11 @@ int ngsld_share_sites(ngsld_ctx *dst, const ngsld_ctx *src) {
   CUDA_TRY(c, peer(c->d_gl, src->d_gl, n * n_pad * 24));
   CUDA_TRY(c, peer(c->d_maf, src->d_maf, n * 8));
   CUDA_TRY(c, peer(c->d_q, src->d_q, n * 8));
-  CUDA_TRY(c, peer(c->d_dx_sig, src->d_dx_sig, n * n_pad * 8));
-  CUDA_TRY(c, peer(c->d_dx_se, src->d_dx_se, n * n_pad * 2));
+  const uint64_t n_blk = (src->n_ind + 3) / 4;
+  CUDA_TRY(c, peer(c->d_dx_sig, src->d_dx_sig, n * n_blk * 4 * 8));
+  CUDA_TRY(c, peer(c->d_dx_se, src->d_dx_se, n * n_blk * 4 * 2));
   CUDA_TRY(c, peer(c->d_seg, src->d_seg, n * 4));
-  CUDA_TRY(c, peer(c->d_ratio, src->d_ratio, (n_pad + 1) * 8));
+  CUDA_TRY(c, peer(c->d_ratio, src->d_ratio, n_blk * 4 * 8));
   if (c->d_cls && src->d_cls) {
     CUDA_TRY(c, peer(c->d_cls, src->d_cls, n * n_cpad));
     CUDA_TRY(c, peer(c->d_pal, src->d_pal, n * (size_t)NGSLD_KMAX * 24));

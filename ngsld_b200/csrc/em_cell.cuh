@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
   double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap, A.kstride) - (size_t)A.tcap * 56);
   wipe_bins(bins, A.kstride, lane);
   const bool ign = A.ignore_miss != 0;
-  unsigned long long my_passes = 0, my_cell_passes = 0, my_cells = 0, my_pairs = 0, my_resid = 0;
+  // work statistics of this warp (passes, cell passes, cells, pairs, pairs left over): kept in shared memory, not in
+  // ten registers that would be live through both phases of every batch
+  __shared__ unsigned long long wstat_all[WARPS_PER_CTA][5];
+  unsigned long long *wstat = wstat_all[warp];
+  if (lane < 5) wstat[lane] = 0;
+  __syncwarp();
 
   const unsigned long long n_batches =
       A.swz_len ? (unsigned long long)A.swz_rows * ((A.swz_len + 31u) / 32u) : (C.n_pairs + 31ull) / 32ull;
@@ -311,8 +316,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
         }
       }
       if (!mine_ok) {  // left to the dense kernel
-        if (lane == 0) A.resid[atomicAdd(&ctr->n_resid, 1ull)] = (uint32_t)idx;
-        my_resid++;
+        if (lane == 0) {
+          A.resid[atomicAdd(&ctr->n_resid, 1ull)] = (uint32_t)idx;
+          wstat[4]++;
+        }
         continue;
       }
       // ---- cells -> registers (slot lane + 32 r) and the shared-memory tail (slots 32 R ...) ----
@@ -365,20 +372,20 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
         for (int k = 0; k < 4; k++)
           gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));
         derive_and_store(C.rows + idx, gq, conv ? it : (uint32_t)NGSLD_ITER_MAX, n_used);
+        wstat[0] += it + 1;
+        wstat[1] += (unsigned long long)(it + 1) * n_cells;
+        wstat[2] += n_cells;
+        wstat[3]++;
       }
-      my_passes += it + 1;
-      my_cell_passes += (unsigned long long)(it + 1) * n_cells;
-      my_cells += n_cells;
-      my_pairs++;
       __syncwarp();  // every lane is done with the tail before the next pair overwrites it
     }
   }
   if (lane == 0) {
-    if (my_passes) atomicAdd(&ctr->em_passes, my_passes);
-    if (my_cell_passes) atomicAdd(&ctr->cell_passes, my_cell_passes);
-    if (my_cells) atomicAdd(&ctr->cells, my_cells);
-    if (my_pairs) atomicAdd(&ctr->cell_pairs, my_pairs);
-    if (my_resid) atomicAdd(&ctr->resid_pairs, my_resid);
+    if (wstat[0]) atomicAdd(&ctr->em_passes, wstat[0]);
+    if (wstat[1]) atomicAdd(&ctr->cell_passes, wstat[1]);
+    if (wstat[2]) atomicAdd(&ctr->cells, wstat[2]);
+    if (wstat[3]) atomicAdd(&ctr->cell_pairs, wstat[3]);
+    if (wstat[4]) atomicAdd(&ctr->resid_pairs, wstat[4]);
   }
 }
 

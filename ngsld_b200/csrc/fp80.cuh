@@ -403,6 +403,167 @@ X87_HD void mac_ratio(ext &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint
   acc.exp = er + (int32_t)carry;
 }
 
+// ---- the same step on 32-bit limbs (what the kernels use) ----------------------------------------------------------
+// mac3 is mac_ratio written for a machine whose registers are 32 bits wide and whose warps pay for every path any lane
+// takes: the significands are two words, the aligned addition runs in a 96-bit window (64 bits + one guard word whose
+// lowest bit collects everything that falls off: "jamming") with ONE bit of headroom on top, so that addition and
+// subtraction are the same three-word two's-complement sum followed by the same count-leading-zeros normalisation, and
+// only two cases leave the straight line: a term more than 2^31 times smaller (or larger) than the running sum, and a
+// cancellation of 31 or more bits.  Results are identical to mac_ratio (tests/native/fp80_check.cpp).
+//
+// Terms come in a packed form of their own ("se14"): bit 15 = sign, bits 0-14 = exponent + 8192 (every deviation of an
+// expected genotype lies within 2^+-1200), so that one integer addition of two such words yields the exponent sum AND
+// (in bit 15: a one-bit sum without carry-in) the sign of the product.
+struct acc96 {   // value = (-1)^neg * (h1:h0) * 2^(exp - ACC_BIAS - 63); zero: h1 == 0 (exp = ACC_ZERO_EXP, neg = 0)
+  uint32_t h1, h0;
+  int32_t exp;
+  uint32_t neg;
+};
+constexpr int32_t ACC_BIAS = 16381;            // (ea + 8192) + (eb + 8192) - 1 (the ratio's exponent) - 2 (see mul_round3)
+constexpr int32_t ACC_ZERO_EXP = -(1 << 28);   // far below every term: the first term then simply wins the comparison
+
+X87_HD uint16_t se14_pack(uint32_t neg, int32_t exp, uint64_t sig) {  // zero <=> 0 (a non-zero term has exp + 8192 > 0)
+  return sig ? (uint16_t)((neg << 15) | ((uint32_t)(exp + 8192) & 0x7fffu)) : (uint16_t)0;
+}
+X87_HD uint16_t se14_from_x87(uint16_t se) {  // from the sign | biased-exponent word of the 80-bit memory image
+  return (uint16_t)((se & 0x8000u) | ((uint32_t)((int32_t)(se & 0x7fffu) - 16383 + 8192) & 0x7fffu));
+}
+
+X87_HD uint32_t fsh_l(uint32_t lo, uint32_t hi, uint32_t s) {  // upper word of (hi:lo) << s, 0 <= s <= 31
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+X87_HD uint32_t fsh_rc(uint32_t lo, uint32_t hi, uint32_t s) {  // lower word of (hi:lo) >> min(s, 32)
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo, hi, s);
+#else
+  return s >= 32 ? hi : (s ? (lo >> s) | (hi << (32 - s)) : lo);
+#endif
+}
+X87_HD uint32_t clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)v);
+#else
+  return v ? (uint32_t)__builtin_clz(v) : 32u;
+#endif
+}
+// r2:r1:r0 = (a2:a1:a0) + (b2:b1:b0), carries rippling upwards (the carry out of the top word is dropped)
+X87_HD void add96(uint32_t a2, uint32_t a1, uint32_t a0, uint32_t b2, uint32_t b1, uint32_t b0, uint32_t &r2, uint32_t &r1,
+                  uint32_t &r0) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+      : "=r"(r0), "=r"(r1), "=r"(r2)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b0), "r"(b1), "r"(b2));
+#else
+  const uint64_t s0 = (uint64_t)a0 + b0, s1 = (uint64_t)a1 + b1 + (s0 >> 32);
+  r0 = (uint32_t)s0;
+  r1 = (uint32_t)s1;
+  r2 = a2 + b2 + (uint32_t)(s1 >> 32);
+#endif
+}
+
+// Rounds the window x1:x0 | g (g = the 32 bits below, lowest bit jammed) to 64 bits, ties to even -> h1:h0 with the top
+// bit set; nw = 0 if the rounding carried out of 64 bits (significand 2^63, exponent one up), else 1.
+X87_HD void round64(uint32_t x1, uint32_t x0, uint32_t g, uint32_t &h1, uint32_t &h0, uint32_t &nw) {
+  const uint32_t rest = (uint32_t)((g & 0x7fffffffu) != 0);
+  const uint32_t inc = (g >> 31) & (rest | x0);
+  const uint32_t y0 = x0 + inc;
+  const uint32_t y1 = x1 + (uint32_t)(y0 < inc);
+  nw = y1 >> 31;           // x1 has its top bit set: only an all-ones significand can wrap, and then to zero
+  h1 = y1 | 0x80000000u;
+  h0 = y0;
+}
+
+// a * b, both normalised, rounded to 64 bits -> h1:h0.  The exponent of the result is ea + eb + 2 - s - nw:
+// s = 1 if the product lay in [2^126, 2^127) (moved one place to the left), nw = 0 if the rounding carried out.
+X87_HD void mul_round3(uint64_t a, uint64_t b, uint32_t &h1, uint32_t &h0, uint32_t &s, uint32_t &nw) {
+  uint64_t hi, lo;
+  mul64(a, b, hi, lo);  // (nvcc shares the partial products of __umul64hi and a * b: seven instructions; spelling the
+                        // schoolbook product out on 32-bit halves compiled to more)
+  const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi, w3 = (uint32_t)(hi >> 32);
+  s = (~w3) >> 31;
+  const uint32_t x1 = fsh_l(w2, w3, s), x0 = fsh_l(w1, w2, s);
+  const uint32_t g = fsh_l(w0, w1, s) | (uint32_t)((w0 << s) != 0);  // the lowest word only matters as "something there"
+  round64(x1, x0, g, h1, h0, nw);
+}
+
+// acc += fl80( fl80(a * b) * r ), r = rsig * 2^-64 in [0.5, 1);  ase / bse in se14 form.
+X87_HD void mac3(acc96 &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
+  if (ase == 0 || bse == 0) return;  // a zero term leaves the sum as it is
+  uint32_t p1, p0, t1, t0, sa, na, sb, nb2;
+  mul_round3(asig, bsig, p1, p0, sa, na);                           // P = fl80(a * b)
+  mul_round3(((uint64_t)p1 << 32) | p0, rsig, t1, t0, sb, nb2);     // T = fl80(P * r)
+  const uint32_t se = ase + bse;
+  const int32_t e = (int32_t)(se & 0x7fffu) - (int32_t)(sa + na) - (int32_t)(sb + nb2);  // biased by ACC_BIAS
+  const uint32_t tneg = (se >> 15) & 1u;
+  // big = operand of larger magnitude
+  const int32_t dd = acc.exp - e;
+  const uint64_t A = ((uint64_t)acc.h1 << 32) | acc.h0, T = ((uint64_t)t1 << 32) | t0;
+  const bool tb = (dd < 0) | ((dd == 0) & (T > A));
+  const uint32_t B1 = tb ? t1 : acc.h1, B0 = tb ? t0 : acc.h0, S1 = tb ? acc.h1 : t1, S0 = tb ? acc.h0 : t0;
+  int32_t eb = tb ? e : acc.exp;
+  const uint32_t sub = acc.neg ^ tneg;
+  acc.neg = tb ? tneg : acc.neg;
+  uint32_t k = (uint32_t)(dd < 0 ? -dd : dd);
+  k = (k > 66u ? 66u : k) + 1u;  // beyond 66 places the small operand cannot matter: any distance above is as good as 66
+  // window of 96 bits, big at bits 94..31 (one bit of headroom), small k places further down
+  uint32_t X1 = fsh_rc(S1, 0u, k), X0 = fsh_rc(S0, S1, k), G = fsh_rc(0u, S0, k);
+  if (k > 32u) {  // (rare) the words above hold the shift by 32; the rest of the way, jamming what falls off
+    const uint32_t k2 = k - 32u;  // 1..35
+    const uint64_t v = ((uint64_t)S1 << 32) | S0;
+    const uint64_t u = v >> k2;
+    X1 = 0;
+    X0 = (uint32_t)(u >> 32);
+    G = (uint32_t)u | (uint32_t)((v << (64u - k2)) != 0);
+  }
+  // big + small, or big - small as big + ~small + 1 (the "+ 1" rides in the 31 empty low bits of big's guard word)
+  const uint32_t m = 0u - sub;
+  uint32_t R1, R0, g;
+  add96(B1 >> 1, fsh_rc(B0, B1, 1u), (B0 << 31) | sub, X1 ^ m, X0 ^ m, G ^ m, R1, R0, g);
+  if (R1 == 0) {  // (rare) 31 or more leading bits cancelled; the guard word then holds at most its two top bits
+    if ((R0 | g) == 0) {  // exact cancellation -> +0
+      acc.h1 = 0;
+      acc.h0 = 0;
+      acc.exp = ACC_ZERO_EXP;
+      acc.neg = 0;
+      return;
+    }
+    if (R0 == 0) {
+      R1 = g;
+      g = 0;
+      eb -= 64;
+    } else {
+      R1 = R0;
+      R0 = g;
+      g = 0;
+      eb -= 32;
+    }
+  }
+  const uint32_t z = clz32(R1);
+  uint32_t nw;
+  round64(fsh_l(R0, R1, z), fsh_l(g, R0, z), g << z, acc.h1, acc.h0, nw);
+  acc.exp = eb + 2 - (int32_t)z - (int32_t)nw;
+}
+
+X87_HD acc96 acc96_zero() {
+  acc96 a;
+  a.h1 = 0;
+  a.h0 = 0;
+  a.exp = ACC_ZERO_EXP;
+  a.neg = 0;
+  return a;
+}
+X87_HD ext acc96_to_ext(const acc96 &a) {
+  ext r;
+  r.sig = ((uint64_t)a.h1 << 32) | a.h0;
+  r.exp = r.sig ? a.exp - ACC_BIAS : 0;
+  r.neg = r.sig ? a.neg : 0u;
+  return r;
+}
+
 // significand of (long double)(i / (i + 1.0)) for i >= 1 (the value lies in [0.5, 1): exponent -1)
 X87_HD uint64_t ratio_sig(double ratio) {
 #if defined(__CUDA_ARCH__)

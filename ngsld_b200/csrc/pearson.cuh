@@ -9,60 +9,38 @@
 #include "common.cuh"
 #include "fp80.cuh"
 
-#ifndef NGSLD_PEARSON_UNROLL2
-#define NGSLD_PEARSON_UNROLL2 0
-#endif
-
 namespace pearson {
 
 __device__ __forceinline__ double pair_r2(const SiteTable &T, uint32_t s1, uint32_t s2) {
-#if NGSLD_PEARSON_UNROLL2
-  // Experiment (not the default: measured together with the straight-line accumulate step it was 3 % slower): two
-  // individuals per trip with two register sets, so that no set is ever copied into the other; the tables have a spare
-  // row behind the last individual, so the request for "the next one" needs no guard.
-  x87::ext acc = x87::zero(0);
-  const size_t stride = T.n_sites;
-  const uint64_t *p1 = T.dx_sig + stride + s1, *p2 = T.dx_sig + stride + s2;  // row i = 1
-  const uint16_t *q1 = T.dx_se + stride + s1, *q2 = T.dx_se + stride + s2;
-  const uint64_t *pr = T.ratio + 1;
-  uint64_t a0 = 0, b0 = 0, r0 = 0, a1, b1, r1;
-  uint32_t ea0 = 0, eb0 = 0, ea1, eb1;
-  if (T.n_ind > 1) {
-    a0 = *p1; b0 = *p2; ea0 = *q1; eb0 = *q2; r0 = __ldg(pr);
+  // Blocks of four individuals (individual 0 and the padding behind the last one are stored as zero terms, which mac3
+  // skips).  One register set, refilled on the fly: as soon as the first two individuals of a block are accumulated, the
+  // first two of the next block are requested into the same registers (then the same for the second two), so every
+  // request has two accumulate steps (~300 instructions) to come back from L2, and nothing is ever copied.  The tables
+  // have one spare block row behind the last one, so the last refill needs no guard.  Record (blk, s) has the index
+  // blk * n_sites + s < 2^32 (a site table of that many 24-byte likelihood triples would not fit the memory).
+  // The four ratios of a block are the same words for every lane and every pair: they sit in L1 and are fetched when
+  // needed instead of travelling through prefetch registers.
+  x87::acc96 acc3 = x87::acc96_zero();
+  const ulonglong2 *SIG = reinterpret_cast<const ulonglong2 *>(T.dx_sig);  // two individuals per element
+  const uint32_t *SE = reinterpret_cast<const uint32_t *>(T.dx_se);        // two individuals per element
+  const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(T.ratio);
+  uint32_t ia = s1, ib = s2;
+  ulonglong2 a01 = SIG[2 * (size_t)ia], a23 = SIG[2 * (size_t)ia + 1], b01 = SIG[2 * (size_t)ib], b23 = SIG[2 * (size_t)ib + 1];
+  uint32_t ea01 = SE[2 * (size_t)ia], ea23 = SE[2 * (size_t)ia + 1], eb01 = SE[2 * (size_t)ib], eb23 = SE[2 * (size_t)ib + 1];
+  for (uint32_t blk = 0; blk < T.n_blk; blk++) {
+    const ulonglong2 r01 = __ldg(pr + 2 * blk), r23 = __ldg(pr + 2 * blk + 1);
+    ia += T.n_sites;
+    ib += T.n_sites;
+    x87::mac3(acc3, a01.x, ea01 & 0xffffu, b01.x, eb01 & 0xffffu, r01.x);
+    x87::mac3(acc3, a01.y, ea01 >> 16, b01.y, eb01 >> 16, r01.y);
+    a01 = SIG[2 * (size_t)ia]; b01 = SIG[2 * (size_t)ib];
+    ea01 = SE[2 * (size_t)ia]; eb01 = SE[2 * (size_t)ib];
+    x87::mac3(acc3, a23.x, ea23 & 0xffffu, b23.x, eb23 & 0xffffu, r23.x);
+    x87::mac3(acc3, a23.y, ea23 >> 16, b23.y, eb23 >> 16, r23.y);
+    a23 = SIG[2 * (size_t)ia + 1]; b23 = SIG[2 * (size_t)ib + 1];
+    ea23 = SE[2 * (size_t)ia + 1]; eb23 = SE[2 * (size_t)ib + 1];
   }
-  for (uint32_t i = 1; i < T.n_ind; i += 2) {
-    p1 += stride; p2 += stride; q1 += stride; q2 += stride; pr++;
-    a1 = *p1; b1 = *p2; ea1 = *q1; eb1 = *q2; r1 = __ldg(pr);
-    x87::mac_ratio(acc, a0, ea0, b0, eb0, r0);
-    if (i + 1 >= T.n_ind) break;
-    p1 += stride; p2 += stride; q1 += stride; q2 += stride; pr++;
-    a0 = *p1; b0 = *p2; ea0 = *q1; eb0 = *q2; r0 = __ldg(pr);
-    x87::mac_ratio(acc, a1, ea1, b1, eb1, r1);
-  }
-#else
-  x87::ext acc = x87::zero(0);
-  // software-pipelined by hand: the operands of individual i + 1 are requested before individual i is accumulated,
-  // otherwise every iteration would wait out a full L2 round trip (the loop body is too branchy for the compiler
-  // to hoist the loads itself)
-  const uint64_t *sig = T.dx_sig + T.n_sites;  // row i = 1
-  const uint16_t *se = T.dx_se + T.n_sites;
-  uint64_t a_sig = 0, b_sig = 0, r_sig = 0;
-  uint32_t a_se = 0, b_se = 0;
-  if (T.n_ind > 1) {
-    a_sig = sig[s1]; b_sig = sig[s2]; a_se = se[s1]; b_se = se[s2]; r_sig = __ldg(T.ratio + 1);
-  }
-  for (uint32_t i = 1; i < T.n_ind; i++) {
-    uint64_t na_sig = 0, nb_sig = 0, nr_sig = 0;
-    uint32_t na_se = 0, nb_se = 0;
-    if (i + 1 < T.n_ind) {
-      sig += T.n_sites;
-      se += T.n_sites;
-      na_sig = sig[s1]; nb_sig = sig[s2]; na_se = se[s1]; nb_se = se[s2]; nr_sig = __ldg(T.ratio + i + 1);
-    }
-    x87::mac_ratio(acc, a_sig, a_se, b_sig, b_se, r_sig);
-    a_sig = na_sig; b_sig = nb_sig; a_se = na_se; b_se = nb_se; r_sig = nr_sig;
-  }
-#endif
+  const x87::ext acc = x87::acc96_to_ext(acc3);
   const double den = __dmul_rn(T.q[s1], T.q[s2]);
   double r;
   if (den == 0.0 || den != den) {

@@ -36,6 +36,20 @@ for stage in "$@"; do
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-em_cell_kernel} -s ${NCU_SKIP:-1} -c 1 -f -o $OUT/${TAG}_${NCU_NAME:-em_cell} \
         python scripts/sweep.py --pairs 4000000 --reps 2 ${NCU_ARGS:-} > $OUT/${TAG}_ncu_${NCU_NAME:-em_cell}.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_${NCU_NAME:-em_cell}.log ;;
+    ab)
+      # A/B of alternative builds of the library (make -C ngsld_b200/csrc ALT=_x ALTFLAGS=... lib): parity tests on each
+      # alternative build, then the same sweep on the default build and on the alternatives
+      for alt in ${AB_LIBS:-_x}; do
+        NGSLD_B200_LIB=$PWD/ngsld_b200/libngsld_b200${alt}.so timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -m gpu -x -q \
+          > $OUT/${TAG}_ab_pytest${alt}.log 2>&1; echo "ab pytest ${alt} rc=$?"; tail -4 $OUT/${TAG}_ab_pytest${alt}.log
+      done
+      for alt in "" ${AB_LIBS:-_x}; do
+        for set in ${AB_SETS:-500:50000}; do  # n_ind:n_sites
+          nind=${set%%:*}; nsites=${set##*:}
+          NGSLD_B200_LIB=$PWD/ngsld_b200/libngsld_b200${alt}.so timeout 600 python scripts/sweep.py --n-ind $nind --n-sites $nsites ${AB_ARGS:-} \
+            > $OUT/${TAG}_ab_sweep${alt}_n${nind}.log 2>&1; echo "ab sweep lib${alt} n_ind=$nind rc=$?"; cat $OUT/${TAG}_ab_sweep${alt}_n${nind}.log | cut -c1-330
+        done
+      done ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
