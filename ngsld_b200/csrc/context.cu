@@ -626,7 +626,10 @@ int choose_cell(ngsld_ctx *c, EmChoice &ch) {
   if (!(path ? c->cell_possible : c->cell_ok)) return NGSLD_OK;
   // cells per lane in registers from the sampled 99.5th percentile; the rest of a pair's cells go to shared memory
   int r = c->cell_p995 <= 64 ? 2 : c->cell_p995 <= 128 ? 4 : 6;
-  int minb = 4;  // CTAs per SM the variant is compiled for: 4 -> 128 registers, 16 warps per SM (measured +14 % over 3 -> 168)
+  // CTAs per SM the variant is compiled for: six register cells per lane need 128 registers (4 CTAs, 16 warps per SM:
+  // measured +14 % over 3 CTAs with 168 registers); with four or two cells per lane 96 registers do, and the fifth CTA
+  // pays (100 individuals, 65 cells per pair: 110 against 102 M pairs/s, round 2)
+  int minb = r <= 4 ? 5 : 4;
   if (const char *e = getenv("NGSLD_CELL_R")) r = atoi(e);
   if (const char *e = getenv("NGSLD_CELL_MINB")) minb = atoi(e);
   const emcell::CellVariant *v = nullptr;

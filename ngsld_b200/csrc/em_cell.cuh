@@ -20,6 +20,9 @@
 //   2. loads the cells -- palette triples + weight -- into registers (R per lane; cells beyond 32 R go to a shared-
 //      memory tail) and zeroes the counters it used;
 //   3. iterates the EM exactly like em_warp.cuh, one weighted E-step per cell.
+// (Step 1 was also tried with shared-memory atomics and a sweep of the table instead of match.any and lane-by-lane counter
+// updates -- the MATCH instruction alone holds 8 % of the kernel's stall samples -- and measured 9 % SLOWER: sixteen
+// atomics per lane and pair compete with the shuffles of the EM reduction for the same data path.  profiles/README.md.)
 // Pairs it cannot take (a site with more than NGSLD_KMAX distinct triples, more cells than the warp has room for) are
 // appended to a list that the dense warp-per-pair kernel processes right afterwards.
 //
@@ -39,6 +42,18 @@
 #endif
 #ifndef NGSLD_CELL_SMEM_BCAST
 #define NGSLD_CELL_SMEM_BCAST 0
+#endif
+// 1: loop bodies without any shared-memory-tail code for pairs that have no tail.  34 instructions fewer per pass (236
+// instead of 270 at six register levels), but measured SLOWER at 500 and 2000 individuals (59.4 vs 61.4 and 22.1 vs 23.0
+// M pairs/s, round 2): in that form ptxas keeps the four haplotype frequencies in vector registers instead of uniform
+// registers, and an FP64 instruction that reads three vector registers issues at 0.72 of the rate of one that reads two.
+#ifndef NGSLD_CELL_NOTAIL_BODIES
+#define NGSLD_CELL_NOTAIL_BODIES 0
+#endif
+// 1: while a pair is iterated, the class row and the palette of the NEXT pair's second site are pulled into L1, so that
+// the construction of its cells does not start with a round trip to L2 (+0.3 % at 500, +1.7 % at 2000 individuals).
+#ifndef NGSLD_CELL_PREFETCH
+#define NGSLD_CELL_PREFETCH 1
 #endif
 
 namespace emcell {
@@ -149,6 +164,15 @@ struct Cell {
   double w;
 };
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// The second site's class row (n_cpad bytes) and palette (pal_k triples): one 128-byte line per lane.
+__device__ __forceinline__ void prefetch_site(const SiteTable &T, uint32_t s, int lane) {
+  const uint32_t off = 128u * (uint32_t)lane;
+  if (off < T.n_cpad) prefetch_l1(T.cls + (size_t)s * T.n_cpad + off);
+  if (off < (uint32_t)NGSLD_KMAX * 24u) prefetch_l1(reinterpret_cast<const char *>(T.pal + (size_t)s * NGSLD_KMAX * 3) + off);
+}
+
 __device__ __forceinline__ void cell_default(Cell &c) {  // an empty slot: weight 0, likelihoods that keep s finite
   c.g.p0 = c.g.p1 = c.g.p2 = c.g.q0 = c.g.q1 = c.g.q2 = 1.0;
   c.w = 0.0;
@@ -201,7 +225,7 @@ __device__ __forceinline__ double warp_sum4_own(double a0, double a1, double a2,
 // of component q, see warp_sum4_own) and the four new frequencies are then broadcast; `fq` / `Aq` are the lane's own
 // component.  Convergence (reference gen_func.cpp:1049-1055): eps = max_k |f_k - f_last_k| < 1e-5 with a NaN difference
 // never raising eps  <=>  no component has |difference| >= 1e-5.  Returns the index of the converging pass.
-template <int L, int R>
+template <int L, int R, bool TAIL>
 __device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double *tail, uint32_t tcap, uint32_t n_tail_pad,
                                                double inv_x, int lane, double &f0, double &f1, double &f2, double &f3,
                                                double &Aq, bool &conv, uint32_t fbuf) {
@@ -211,7 +235,7 @@ __device__ __forceinline__ uint32_t em_iterate(const Cell (&g)[R], const double 
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
     for (int r = 0; r < L; r++) cell_step(f0, f1, f2, f3, g[r], a0, a1, a2, a3);
-    for (uint32_t t = lane; t < n_tail_pad; t += 64u) {  // two cells per lane and trip
+    if (TAIL) for (uint32_t t = lane; t < n_tail_pad; t += 64u) {  // two cells per lane and trip
       Cell c, d;
       c.g.p0 = tail[0 * tcap + t]; c.g.p1 = tail[1 * tcap + t]; c.g.p2 = tail[2 * tcap + t];
       c.g.q0 = tail[3 * tcap + t]; c.g.q1 = tail[4 * tcap + t]; c.g.q2 = tail[5 * tcap + t];
@@ -265,6 +289,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
   double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap, A.kstride) - (size_t)A.tcap * 56);
   wipe_bins(bins, A.kstride, lane);
   const bool ign = A.ignore_miss != 0;
+  // Results of the batch's EMs wait here (per pair: the four warp totals A_k of the last pass, n_used, nIter) until the
+  // whole batch is iterated; then every lane finishes ONE pair -- the output M-step with its eight true divisions and
+  // D, D', r2, chi2 (another six divisions and a square root) -- instead of lane 0 doing that for every pair while 31
+  // lanes wait (~600 instructions per pair in a single lane: measured +8 % for the whole kernel, round 2).
+  __shared__ __align__(16) double stageA_all[WARPS_PER_CTA][32][4];
+  __shared__ uint2 stageB_all[WARPS_PER_CTA][32];
+  double(*stageA)[4] = stageA_all[warp];
+  uint2 *stageB = stageB_all[warp];
   // work statistics of this warp (passes, cell passes, cells, pairs, pairs left over): kept in shared memory, not in
   // ten registers that would be live through both phases of every batch
   __shared__ unsigned long long wstat_all[WARPS_PER_CTA][5];
@@ -302,6 +334,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
     const int nb = (int)width;
 
     // ---- the batch's EMs, the whole warp on one pair at a time ----
+    uint32_t done = 0;  // bit j: pair j of the batch was iterated here (not left to the dense kernel)
     for (int j = 0; j < nb; j++) {
       const uint32_t s1 = __shfl_sync(0xffffffffu, my_s1, j), s2 = __shfl_sync(0xffffffffu, my_s2, j);
       const unsigned long long idx = base + j;
@@ -343,6 +376,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       }
       __syncwarp();
 
+#if NGSLD_CELL_PREFETCH
+      if (j + 1 < nb) prefetch_site(T, __shfl_sync(0xffffffffu, my_s2, j + 1), lane);
+#endif
       const double inv_x = __ddiv_rn(1.0, (double)n_used);
       const double m1 = T.maf[s1], m2 = T.maf[s2];  // haplo_freq start point, gen_func.cpp:1034-1037
       double f0 = __dmul_rn(__dsub_rn(1.0, m1), __dsub_rn(1.0, m2));
@@ -352,33 +388,44 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
       double Aq = 0;
       uint32_t it = 0;
       bool conv = false;
-      switch (n_lev) {  // warp-uniform; empty register levels are skipped as a whole
-        case 0: it = em_iterate<0, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        case 1: it = em_iterate<1, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        case 2: it = em_iterate<(R < 2 ? R : 2), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        case 3: it = em_iterate<(R < 3 ? R : 3), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        case 4: it = em_iterate<(R < 4 ? R : 4), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        case 5: it = em_iterate<(R < 5 ? R : 5), R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
-        default: it = em_iterate<R, R>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+      // warp-uniform choice of the loop body: empty register levels are skipped as a whole (only a pair that fills every
+      // register level can have cells in the shared-memory tail: n_tail_pad is 0 for the others)
+      static_assert(R <= 6, "the switch below lists register levels 0..6");
+      constexpr bool NT = NGSLD_CELL_NOTAIL_BODIES != 0;  // bodies for pairs without a tail carry no tail code
+      switch (NT && n_tail ? 99u : n_lev) {
+        case 0: it = em_iterate<0, R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 1: it = em_iterate<1, R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 2: it = em_iterate<(R < 2 ? R : 2), R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 3: it = em_iterate<(R < 3 ? R : 3), R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 4: it = em_iterate<(R < 4 ? R : 4), R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 5: it = em_iterate<(R < 5 ? R : 5), R, !NT>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
+        case 6: if (NT) { it = em_iterate<(R < 6 ? R : 6), R, false>(g, tail, A.tcap, 0, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break; }
+        default: it = em_iterate<R, R, true>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
       }
-      const double A0 = __shfl_sync(0xffffffffu, Aq, 0), A1 = __shfl_sync(0xffffffffu, Aq, 8),
-                   A2 = __shfl_sync(0xffffffffu, Aq, 16), A3 = __shfl_sync(0xffffffffu, Aq, 24);
+      if ((lane & 7) == 0) stageA[j][lane >> 3] = Aq;  // the first lane of each quadrant holds the total of its component
       if (lane == 0) {
-        // Output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113): true divisions and the
-        // sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes.
-        const double xd = (double)n_used;
-        double gq[4] = {__ddiv_rn(A0, xd), __ddiv_rn(A1, xd), __ddiv_rn(A2, xd), __ddiv_rn(A3, xd)};
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));
-        derive_and_store(C.rows + idx, gq, conv ? it : (uint32_t)NGSLD_ITER_MAX, n_used);
+        stageB[j] = make_uint2(n_used, conv ? it : (uint32_t)NGSLD_ITER_MAX);
         wstat[0] += it + 1;
         wstat[1] += (unsigned long long)(it + 1) * n_cells;
         wstat[2] += n_cells;
         wstat[3]++;
       }
+      done |= 1u << j;
       __syncwarp();  // every lane is done with the tail before the next pair overwrites it
     }
+    // ---- one pair per lane: output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113: true divisions and
+    // the sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes), then D, D', r2, chi2
+    if ((done >> lane) & 1u) {
+      const uint2 sb = stageB[lane];
+      const double xd = (double)sb.x;
+      double gq[4] = {__ddiv_rn(stageA[lane][0], xd), __ddiv_rn(stageA[lane][1], xd), __ddiv_rn(stageA[lane][2], xd),
+                      __ddiv_rn(stageA[lane][3], xd)};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));
+      derive_and_store(C.rows + base + lane, gq, sb.y, sb.x);
+    }
+    __syncwarp();  // the staging area is free again
   }
   if (lane == 0) {
     if (wstat[0]) atomicAdd(&ctr->em_passes, wstat[0]);

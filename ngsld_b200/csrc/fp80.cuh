@@ -490,15 +490,30 @@ X87_HD void mul_round3(uint64_t a, uint64_t b, uint32_t &h1, uint32_t &h0, uint3
   round64(x1, x0, g, h1, h0, nw);
 }
 
-// acc += fl80( fl80(a * b) * r ), r = rsig * 2^-64 in [0.5, 1);  ase / bse in se14 form.
-X87_HD void mac3(acc96 &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
-  if (ase == 0 || bse == 0) return;  // a zero term leaves the sum as it is
-  uint32_t p1, p0, t1, t0, sa, na, sb, nb2;
-  mul_round3(asig, bsig, p1, p0, sa, na);                           // P = fl80(a * b)
-  mul_round3(((uint64_t)p1 << 32) | p0, rsig, t1, t0, sb, nb2);     // T = fl80(P * r)
-  const uint32_t se = ase + bse;
-  const int32_t e = (int32_t)(se & 0x7fffu) - (int32_t)(sa + na) - (int32_t)(sb + nb2);  // biased by ACC_BIAS
-  const uint32_t tneg = (se >> 15) & 1u;
+// One term of the sum: T = fl80( fl80(a * b) * r ), r = rsig * 2^-64 in [0.5, 1);  ase / bse in se14 form.
+// Straight-line code without a branch, so that the terms of several individuals (which do not depend on each other, only
+// the additions do) can be scheduled into each other.  se == 0 marks a zero term (t1:t0 is then meaningless).
+struct term96 {
+  uint32_t t1, t0;
+  uint32_t se;  // bit 15: sign, bits 0-14: exponent biased by ACC_BIAS; 0: the term is zero
+};
+X87_HD term96 term3(uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
+  uint32_t p1, p0, sa, na, sb, nb2;
+  term96 t;
+  mul_round3(asig, bsig, p1, p0, sa, na);                            // P = fl80(a * b)
+  mul_round3(((uint64_t)p1 << 32) | p0, rsig, t.t1, t.t0, sb, nb2);  // T = fl80(P * r)
+  const uint32_t se = ase + bse;  // exponent sum in bits 0-14 (no carry into bit 15: both fields are below 2^14), sign in bit 15
+  const uint32_t e = (se & 0x7fffu) - (sa + na) - (sb + nb2);  // >= 2 * (8192 - 1200) - 4: far from wrapping
+  t.se = (ase == 0 || bse == 0) ? 0u : ((se & 0x8000u) | e);
+  return t;
+}
+
+// acc += T
+X87_HD void acc3(acc96 &acc, const term96 &tm) {
+  if (tm.se == 0) return;  // a zero term leaves the sum as it is
+  const uint32_t t1 = tm.t1, t0 = tm.t0;
+  const int32_t e = (int32_t)(tm.se & 0x7fffu);
+  const uint32_t tneg = tm.se >> 15;
   // big = operand of larger magnitude
   const int32_t dd = acc.exp - e;
   const uint64_t A = ((uint64_t)acc.h1 << 32) | acc.h0, T = ((uint64_t)t1 << 32) | t0;
@@ -546,6 +561,11 @@ X87_HD void mac3(acc96 &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_
   uint32_t nw;
   round64(fsh_l(R0, R1, z), fsh_l(g, R0, z), g << z, acc.h1, acc.h0, nw);
   acc.exp = eb + 2 - (int32_t)z - (int32_t)nw;
+}
+
+// acc += fl80( fl80(a * b) * r )
+X87_HD void mac3(acc96 &acc, uint64_t asig, uint32_t ase, uint64_t bsig, uint32_t bse, uint64_t rsig) {
+  acc3(acc, term3(asig, ase, bsig, bse, rsig));
 }
 
 X87_HD acc96 acc96_zero() {

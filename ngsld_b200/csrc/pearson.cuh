@@ -9,13 +9,19 @@
 #include "common.cuh"
 #include "fp80.cuh"
 
+// 1: the four terms of a block of individuals are formed first (their multiplications interleave), then added one after the
+// other; 0: term, add, term, add ...
+#ifndef NGSLD_X87_ILP
+#define NGSLD_X87_ILP 1
+#endif
+
 namespace pearson {
 
 __device__ __forceinline__ double pair_r2(const SiteTable &T, uint32_t s1, uint32_t s2) {
   // Blocks of four individuals (individual 0 and the padding behind the last one are stored as zero terms, which mac3
-  // skips).  One register set, refilled on the fly: as soon as the first two individuals of a block are accumulated, the
-  // first two of the next block are requested into the same registers (then the same for the second two), so every
-  // request has two accumulate steps (~300 instructions) to come back from L2, and nothing is ever copied.  The tables
+  // skips).  One register set, refilled on the fly: as soon as the four terms of a block are formed, the next block is
+  // requested into the same registers, so every request has the four additions (~300 instructions) to come back from L2,
+  // and nothing is ever copied.  The tables
   // have one spare block row behind the last one, so the last refill needs no guard.  Record (blk, s) has the index
   // blk * n_sites + s < 2^32 (a site table of that many 24-byte likelihood triples would not fit the memory).
   // The four ratios of a block are the same words for every lane and every pair: they sit in L1 and are fetched when
@@ -31,6 +37,22 @@ __device__ __forceinline__ double pair_r2(const SiteTable &T, uint32_t s1, uint3
     const ulonglong2 r01 = __ldg(pr + 2 * blk), r23 = __ldg(pr + 2 * blk + 1);
     ia += T.n_sites;
     ib += T.n_sites;
+#if NGSLD_X87_ILP
+    // the four terms first (independent of each other and of the sum: the compiler interleaves their multiplications),
+    // then the four additions, which are the sequential part
+    const x87::term96 t0 = x87::term3(a01.x, ea01 & 0xffffu, b01.x, eb01 & 0xffffu, r01.x);
+    const x87::term96 t1 = x87::term3(a01.y, ea01 >> 16, b01.y, eb01 >> 16, r01.y);
+    const x87::term96 t2 = x87::term3(a23.x, ea23 & 0xffffu, b23.x, eb23 & 0xffffu, r23.x);
+    const x87::term96 t3 = x87::term3(a23.y, ea23 >> 16, b23.y, eb23 >> 16, r23.y);
+    a01 = SIG[2 * (size_t)ia]; b01 = SIG[2 * (size_t)ib];
+    ea01 = SE[2 * (size_t)ia]; eb01 = SE[2 * (size_t)ib];
+    a23 = SIG[2 * (size_t)ia + 1]; b23 = SIG[2 * (size_t)ib + 1];
+    ea23 = SE[2 * (size_t)ia + 1]; eb23 = SE[2 * (size_t)ib + 1];
+    x87::acc3(acc3, t0);
+    x87::acc3(acc3, t1);
+    x87::acc3(acc3, t2);
+    x87::acc3(acc3, t3);
+#else
     x87::mac3(acc3, a01.x, ea01 & 0xffffu, b01.x, eb01 & 0xffffu, r01.x);
     x87::mac3(acc3, a01.y, ea01 >> 16, b01.y, eb01 >> 16, r01.y);
     a01 = SIG[2 * (size_t)ia]; b01 = SIG[2 * (size_t)ib];
@@ -39,6 +61,7 @@ __device__ __forceinline__ double pair_r2(const SiteTable &T, uint32_t s1, uint3
     x87::mac3(acc3, a23.y, ea23 >> 16, b23.y, eb23 >> 16, r23.y);
     a23 = SIG[2 * (size_t)ia + 1]; b23 = SIG[2 * (size_t)ib + 1];
     ea23 = SE[2 * (size_t)ia + 1]; eb23 = SE[2 * (size_t)ib + 1];
+#endif
   }
   const x87::ext acc = x87::acc96_to_ext(acc3);
   const double den = __dmul_rn(T.q[s1], T.q[s2]);
