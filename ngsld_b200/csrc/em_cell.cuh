@@ -116,6 +116,59 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
     }
   }
 #endif
+#ifndef NGSLD_CELL_MATCH4
+#define NGSLD_CELL_MATCH4 1
+#endif
+#if NGSLD_CELL_MATCH4
+  // The class words of block k + 1 are requested before block k is counted, and the four match.any of a block -- they
+  // depend on the keys only, not on the counters -- are issued back to back before the four counter updates, which are
+  // the sequential part: the MATCH instruction is slow (it alone held 8 % of the kernel's stall samples when every
+  // update waited for its own match).
+  uint32_t nw1 = 0, nw2 = 0;
+  if (4u * (uint32_t)lane < T.n_ind) {
+    nw1 = *reinterpret_cast<const uint32_t *>(c1 + 4u * (uint32_t)lane);
+    nw2 = *reinterpret_cast<const uint32_t *>(c2 + 4u * (uint32_t)lane);
+  }
+  for (uint32_t blk = 0; blk < T.n_ind; blk += 128u) {
+    const uint32_t i0 = blk + 4u * (uint32_t)lane;  // this lane's four individuals of the block
+    const uint32_t w1 = nw1, w2 = nw2;
+    if (i0 + 128u < T.n_ind) {
+      nw1 = *reinterpret_cast<const uint32_t *>(c1 + i0 + 128u);
+      nw2 = *reinterpret_cast<const uint32_t *>(c2 + i0 + 128u);
+    }
+    uint32_t key[4], peers[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const uint32_t a = (w1 >> (8 * e)) & 255u, b = (w2 >> (8 * e)) & 255u;
+      bool valid = i0 + e < T.n_ind;
+      if (valid && ign) valid = !((((miss1 >> a) | (miss2 >> b)) & 1ull) != 0);
+      key[e] = valid ? (a << 8 | b) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) peers[e] = __match_any_sync(0xffffffffu, key[e]);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const bool valid = key[e] != 0xffffffffu;
+      const bool lead = valid && (__ffs(peers[e]) - 1 == lane);
+      bool fresh = false;
+      if (lead) {
+        const uint32_t bin = (key[e] >> 8) * kstride + (key[e] & 255u);
+        const uint32_t old = bins[bin];
+        bins[bin] = (uint16_t)(old + __popc(peers[e]));
+        fresh = old == 0;
+      }
+      const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
+      if (fresh) {
+        const uint32_t slot = n_cells + __popc(fm & lt);
+        if (slot < cap) keys[slot] = (uint16_t)key[e];
+      }
+      n_cells += __popc(fm);
+      if (ign) used += __popc(__ballot_sync(0xffffffffu, valid));  // (without ignore_miss everybody is counted)
+      __syncwarp();  // the counters written here are read by whichever lane leads the key next time
+    }
+  }
+  if (!ign) used = T.n_ind;
+#else
   for (uint32_t blk = 0; blk < T.n_ind; blk += 128u) {
     const uint32_t i0 = blk + 4u * (uint32_t)lane;  // this lane's four individuals of the block
     uint32_t w1 = 0, w2 = 0;
@@ -155,6 +208,7 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
       __syncwarp();  // the counters written here are read by whichever lane leads the key next time
     }
   }
+#endif
   n_used = used;
   return n_cells;
 }

@@ -117,6 +117,14 @@ int main(int argc, char **argv) {
       (void)ea; (void)eb;
     }
   }
+  // the packed sign/exponent word of the kernels' term tables: from the 80-bit memory image and from (sign, exponent)
+  for (int e = -8000; e <= 8000; e += 7)
+    for (uint32_t neg = 0; neg < 2; neg++) {
+      const uint16_t x87se = (uint16_t)((neg << 15) | (uint32_t)(e + 16383));
+      const uint16_t a = x87::se14_from_x87(x87se), b = x87::se14_pack(neg, e, 1ull << 63);
+      if (a != b || (a >> 15) != neg || (int)(a & 0x7fff) - 8192 != e || a == 0) { if (bad++ < 5) printf("se14 mismatch e=%d\n", e); }
+    }
+  if (x87::se14_pack(1, 5, 0) != 0) { if (bad++ < 5) printf("se14 of a zero term must be 0\n"); }
   // the per-site half of gsl_stats_correlation as aux::site_terms_kernel performs it, against native long double
   std::uniform_real_distribution<double> E(0.0, 2.0);
   for (int rep = 0; rep < 300; rep++) {
