@@ -50,6 +50,15 @@ for stage in "$@"; do
             > $OUT/${TAG}_ab_sweep${alt}_n${nind}.log 2>&1; echo "ab sweep lib${alt} n_ind=$nind rc=$?"; cat $OUT/${TAG}_ab_sweep${alt}_n${nind}.log | cut -c1-330
         done
       done ;;
+    contract)
+      # numerics contract at scale: fast kernel vs bit-faithful kernel on ~40 M pairs of the bench workload
+      timeout 1200 python scripts/contract_at_scale.py > $OUT/${TAG}_contract_at_scale.log 2>&1; echo "contract rc=$?"; tail -4 $OUT/${TAG}_contract_at_scale.log | cut -c1-600 ;;
+    configs)
+      # BASELINE configs 2, 4, 5 scaled to one GPU (results left in HBM): pairs/s per configuration
+      { timeout 600 python scripts/run_config.py --n-sites 10000 --n-ind 100;
+        timeout 900 python scripts/run_config.py --n-sites 100000 --n-ind 1000 --max-kb-dist 500;
+        timeout 900 python scripts/run_config.py --n-sites 60000 --n-ind 2000 --rnd-sample 0.01 --seed 1; } > $OUT/${TAG}_scaled_configs.log 2>&1
+      echo "configs rc=$?"; grep -v "^$" $OUT/${TAG}_scaled_configs.log | cut -c1-400 | tail -12 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
