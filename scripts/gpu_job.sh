@@ -59,6 +59,9 @@ for stage in "$@"; do
         timeout 900 python scripts/run_config.py --n-sites 100000 --n-ind 1000 --max-kb-dist 500;
         timeout 900 python scripts/run_config.py --n-sites 60000 --n-ind 2000 --rnd-sample 0.01 --seed 1; } > $OUT/${TAG}_scaled_configs.log 2>&1
       echo "configs rc=$?"; grep -v "^$" $OUT/${TAG}_scaled_configs.log | cut -c1-400 | tail -12 ;;
+    parity2)
+      # BASELINE config 2 at full size: unmodified reference vs the CLI (strict: md5 of the sorted outputs; fast: contract)
+      timeout 2000 bash scripts/full_parity_config2.sh > $OUT/${TAG}_full_parity_config2.log 2>&1; echo "parity2 rc=$?"; cat $OUT/${TAG}_full_parity_config2.log | cut -c1-300 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
