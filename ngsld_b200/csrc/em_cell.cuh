@@ -34,12 +34,9 @@
 #include "em_fast.cuh"
 #include "pearson.cuh"
 
-// compile-time experiment switches (A/B builds: make ALT=... in csrc/Makefile)
-// Both measured SLOWER than the plain forms at the 128-register budget of the default variant (53.5 vs 58.2 M pairs/s with
-// both on, round 2): they stay off.
-#ifndef NGSLD_CELL_PRELOAD
-#define NGSLD_CELL_PRELOAD 0
-#endif
+// compile-time experiment switches (A/B builds: make ALT=_x ALTFLAGS=-D... lib in csrc/Makefile, scripts/gpu_job.sh ab)
+// 1: the four new frequencies of a pass go round through shared memory instead of eight shuffles.  Measured slower
+// (53.5 vs 58.2 M pairs/s together with a preload of the class words, round 2): stays off.
 #ifndef NGSLD_CELL_SMEM_BCAST
 #define NGSLD_CELL_SMEM_BCAST 0
 #endif
@@ -54,6 +51,11 @@
 // the construction of its cells does not start with a round trip to L2 (+0.3 % at 500, +1.7 % at 2000 individuals).
 #ifndef NGSLD_CELL_PREFETCH
 #define NGSLD_CELL_PREFETCH 1
+#endif
+// 1: joint classes with the class words of the next block of individuals requested ahead and the four match.any of a
+// block issued together; 0: one match per counter update (+2 % at 500, +10 % at 2000 individuals for 1, round 2).
+#ifndef NGSLD_CELL_MATCH4
+#define NGSLD_CELL_MATCH4 1
 #endif
 
 namespace emcell {
@@ -102,23 +104,6 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
   const uint64_t miss1 = ign ? T.pal_miss[s1] : 0ull, miss2 = ign ? T.pal_miss[s2] : 0ull;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t n_cells = 0, used = 0;
-#if NGSLD_CELL_PRELOAD
-  // the class words of the first four blocks (512 individuals) are requested together, ahead of the counting loop: one
-  // trip to L2 instead of one per block
-  uint32_t pre1[4], pre2[4];
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const uint32_t i0 = 128u * b + 4u * (uint32_t)lane;
-    pre1[b] = pre2[b] = 0;
-    if (i0 < T.n_ind) {
-      pre1[b] = *reinterpret_cast<const uint32_t *>(c1 + i0);
-      pre2[b] = *reinterpret_cast<const uint32_t *>(c2 + i0);
-    }
-  }
-#endif
-#ifndef NGSLD_CELL_MATCH4
-#define NGSLD_CELL_MATCH4 1
-#endif
 #if NGSLD_CELL_MATCH4
   // The class words of block k + 1 are requested before block k is counted, and the four match.any of a block -- they
   // depend on the keys only, not on the counters -- are issued back to back before the four counter updates, which are
@@ -172,13 +157,6 @@ __device__ __forceinline__ uint32_t joint_classes(const SiteTable &T, uint32_t s
   for (uint32_t blk = 0; blk < T.n_ind; blk += 128u) {
     const uint32_t i0 = blk + 4u * (uint32_t)lane;  // this lane's four individuals of the block
     uint32_t w1 = 0, w2 = 0;
-#if NGSLD_CELL_PRELOAD
-    if (blk < 512u) {  // (warp-uniform; the loop is not unrolled, so the four words are picked by comparison)
-      const uint32_t b = blk >> 7;
-      w1 = b == 0 ? pre1[0] : b == 1 ? pre1[1] : b == 2 ? pre1[2] : pre1[3];
-      w2 = b == 0 ? pre2[0] : b == 1 ? pre2[1] : b == 2 ? pre2[2] : pre2[3];
-    } else
-#endif
     if (i0 < T.n_ind) {
       w1 = *reinterpret_cast<const uint32_t *>(c1 + i0);
       w2 = *reinterpret_cast<const uint32_t *>(c2 + i0);
