@@ -52,6 +52,12 @@
 #ifndef NGSLD_CELL_PREFETCH
 #define NGSLD_CELL_PREFETCH 1
 #endif
+// 1: the per-pair totals wait for the end of the batch in the pair's own output row (global memory, L2) instead of 5 KB of
+// shared memory per CTA.  Meant to make room for a fourth CTA per SM when the tail holds 192 cells (2000 individuals, where
+// ncu shows three); measured the same there (27.10 vs 27.13 M pairs/s) and -0.3 % at 500 individuals: stays off.
+#ifndef NGSLD_CELL_STAGE_GLOBAL
+#define NGSLD_CELL_STAGE_GLOBAL 0
+#endif
 // 1: joint classes with the class words of the next block of individuals requested ahead and the four match.any of a
 // block issued together; 0: one match per counter update (+2 % at 500, +10 % at 2000 individuals for 1, round 2).
 #ifndef NGSLD_CELL_MATCH4
@@ -321,14 +327,17 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
   double *tail = reinterpret_cast<double *>(mine + warp_smem_bytes(R, A.tcap, A.kstride) - (size_t)A.tcap * 56);
   wipe_bins(bins, A.kstride, lane);
   const bool ign = A.ignore_miss != 0;
-  // Results of the batch's EMs wait here (per pair: the four warp totals A_k of the last pass, n_used, nIter) until the
-  // whole batch is iterated; then every lane finishes ONE pair -- the output M-step with its eight true divisions and
-  // D, D', r2, chi2 (another six divisions and a square root) -- instead of lane 0 doing that for every pair while 31
-  // lanes wait (~600 instructions per pair in a single lane: measured +8 % for the whole kernel, round 2).
+  // Results of the batch's EMs wait (per pair: the four warp totals A_k of the last pass, n_used, nIter) until the whole
+  // batch is iterated; then every lane finishes ONE pair -- the output M-step with its eight true divisions and D, D',
+  // r2, chi2 (another six divisions and a square root) -- instead of lane 0 doing that for every pair while 31 lanes
+  // wait (~600 instructions per pair in a single lane: measured +8 % for the whole kernel, round 2).  They wait in the
+  // pair's own output row (hap[] <- A_k; n_used and nIter are final already) or, NGSLD_CELL_STAGE_GLOBAL = 0, in shared memory.
+#if !NGSLD_CELL_STAGE_GLOBAL
   __shared__ __align__(16) double stageA_all[WARPS_PER_CTA][32][4];
   __shared__ uint2 stageB_all[WARPS_PER_CTA][32];
   double(*stageA)[4] = stageA_all[warp];
   uint2 *stageB = stageB_all[warp];
+#endif
   // work statistics of this warp (passes, cell passes, cells, pairs, pairs left over): kept in shared memory, not in
   // ten registers that would be live through both phases of every batch
   __shared__ unsigned long long wstat_all[WARPS_PER_CTA][5];
@@ -434,9 +443,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
         case 6: if (NT) { it = em_iterate<(R < 6 ? R : 6), R, false>(g, tail, A.tcap, 0, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break; }
         default: it = em_iterate<R, R, true>(g, tail, A.tcap, n_tail_pad, inv_x, lane, f0, f1, f2, f3, Aq, conv, fbuf); break;
       }
-      if ((lane & 7) == 0) stageA[j][lane >> 3] = Aq;  // the first lane of each quadrant holds the total of its component
+#if NGSLD_CELL_STAGE_GLOBAL
+      if ((lane & 7) == 0) C.rows[idx].hap[lane >> 3] = Aq;  // the first lane of each quadrant holds the total of its component
+      if (lane == 0) {
+        C.rows[idx].n_used = n_used;
+        C.rows[idx].n_iter = conv ? it : (uint32_t)NGSLD_ITER_MAX;
+#else
+      if ((lane & 7) == 0) stageA[j][lane >> 3] = Aq;
       if (lane == 0) {
         stageB[j] = make_uint2(n_used, conv ? it : (uint32_t)NGSLD_ITER_MAX);
+#endif
         wstat[0] += it + 1;
         wstat[1] += (unsigned long long)(it + 1) * n_cells;
         wstat[2] += n_cells;
@@ -448,10 +464,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) em_cell_kernel(SiteTable T,
     // ---- one pair per lane: output M-step in the reference's own arithmetic (gen_func.cpp:1108-1113: true divisions and
     // the sequential renormalisation, so exactly-degenerate pairs land on the same 0/0 -> NaN outcomes), then D, D', r2, chi2
     if ((done >> lane) & 1u) {
+#if NGSLD_CELL_STAGE_GLOBAL
+      const ngsld_pair_row *row = C.rows + base + lane;  // written by this warp before the __syncwarp that ended the last pair
+      const uint2 sb = make_uint2(row->n_used, row->n_iter);
+      const double A0 = row->hap[0], A1 = row->hap[1], A2 = row->hap[2], A3 = row->hap[3];
+#else
       const uint2 sb = stageB[lane];
+      const double A0 = stageA[lane][0], A1 = stageA[lane][1], A2 = stageA[lane][2], A3 = stageA[lane][3];
+#endif
       const double xd = (double)sb.x;
-      double gq[4] = {__ddiv_rn(stageA[lane][0], xd), __ddiv_rn(stageA[lane][1], xd), __ddiv_rn(stageA[lane][2], xd),
-                      __ddiv_rn(stageA[lane][3], xd)};
+      double gq[4] = {__ddiv_rn(A0, xd), __ddiv_rn(A1, xd), __ddiv_rn(A2, xd), __ddiv_rn(A3, xd)};
 #pragma unroll
       for (int k = 0; k < 4; k++)
         gq[k] = __ddiv_rn(gq[k], __dadd_rn(__dadd_rn(__dadd_rn(gq[0], gq[1]), gq[2]), gq[3]));

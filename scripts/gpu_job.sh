@@ -39,7 +39,7 @@ for stage in "$@"; do
     ab)
       # A/B of alternative builds of the library (make -C ngsld_b200/csrc ALT=_x ALTFLAGS=... lib): parity tests on each
       # alternative build, then the same sweep on the default build and on the alternatives
-      for alt in ${AB_LIBS:-_x}; do
+      for alt in ${AB_PYTEST_LIBS-${AB_LIBS:-_x}}; do
         NGSLD_B200_LIB=$PWD/ngsld_b200/libngsld_b200${alt}.so timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -m gpu -x -q \
           > $OUT/${TAG}_ab_pytest${alt}.log 2>&1; echo "ab pytest ${alt} rc=$?"; tail -4 $OUT/${TAG}_ab_pytest${alt}.log
       done
