@@ -220,6 +220,9 @@ int ensure_chunks(ngsld_ctx *c, uint64_t rows, bool need_host, bool need_text, u
 // expected-genotype matrix, which only ngsld_set_sites needs (input of the per-site x87 recurrence).
 int alloc_site_buffers(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind, bool with_expg) {
   const uint64_t n_pad = (n_ind + 1) & ~1ull, n_cpad = (n_ind + 15) & ~15ull;
+  // pearson::pair_r2 addresses the records of the x87 term tables with 32-bit indices (block * n_sites + site); a site table
+  // of that many likelihood triples (> 400 GB) would not fit any GPU anyway
+  if (((n_ind + 3) / 4 + 1) * n_sites > 0xffffffffull) return fail(c, NGSLD_E_INVALID, "site table too large (n_sites * n_ind)");
   const size_t row_bytes = n_pad * 24;
   if (n_sites != c->n_sites || n_ind != c->n_ind || !c->d_gl) {
     dfree(c->d_gl);
@@ -238,7 +241,6 @@ int alloc_site_buffers(ngsld_ctx *c, uint64_t n_sites, uint64_t n_ind, bool with
     CUDA_TRY(c, cudaMalloc(&c->d_gl, n_sites * row_bytes));
     CUDA_TRY(c, cudaMalloc(&c->d_maf, n_sites * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_q, n_sites * sizeof(double)));
-    // (one spare row / entry behind the tables: the r2_ExpG loop requests the operands of individual i + 1 unconditionally)
     const uint64_t n_blk = (n_ind + 3) / 4;  // x87 terms: blocks of four individuals
     // (one spare block row behind the last: pearson::pair_r2 requests "the next block" without a guard)
     CUDA_TRY(c, cudaMalloc(&c->d_dx_sig, n_sites * (n_blk + 1) * 4 * sizeof(uint64_t)));
